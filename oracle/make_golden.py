@@ -1,0 +1,117 @@
+"""ORACLE TOOLING (container-only): generate ``tests/golden/*.npz`` from the UNMODIFIED reference.
+
+    python -m oracle.make_golden            # needs /root/reference
+
+Every fixture stores, per control step, the synthetic simulator state that was injected and
+everything the reference produced, so that both ``oracle/shifu_oracle.py`` and the CUDA path can be
+replayed against it without the reference tree (which does not exist on the GPU box).
+
+Crafted micro-cases inside ``a1_small``: identity quaternion (env 4), 90-degree yaw
+(env 5), base contact force of norm exactly 1.0 (envs 6, 7: must NOT terminate), robots far off the
+height map (envs 1-3, index clamps), ``ep_len`` 499/500/501 boundary (envs 8-10), terrain-level
+up / down / wrap-around (random initial levels incl. max-1), all-envs reset (record 0 is
+``env.reset()``), and a step with zero resets (step 5; ``extras`` must persist).
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+
+from oracle import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(_REPO, "tests", "golden")
+SMALL_TERRAIN = dict(num_rows=3, num_cols=4, border_size=5, max_init_terrain_level=2)
+ZERO_RESET_STEP = 5
+
+
+def small_hook(step, snap):
+    """Crafted rows, see module docstring."""
+    r = snap.root_offset
+    r[4, 3:7] = torch.tensor([0., 0., 0., 1.])
+    s = float(np.sin(np.pi / 4))
+    r[5, 3:7] = torch.tensor([0., 0., s, s])
+    snap.contact[6, 0] = torch.tensor([1.0, 0.0, 0.0])
+    snap.contact[7, 0] = torch.tensor([0.6, 0.8, 0.0])
+    if step == ZERO_RESET_STEP:
+        snap.contact[:, 0] = 0.
+
+
+def _pack(prefix, d, out):
+    for k, v in d.items():
+        out[f"{prefix}/{k}"] = v
+
+
+def gen_a1(ns, name, n, steps, terrain, seed, store_map, hook=None, snap_kw=None):
+    env = rh.make_a1(ns, n, terrain=terrain)
+    isg = env.isg_env
+    rs = np.random.RandomState(seed)
+    ep = rs.randint(0, 480, size=n).astype(np.int64)
+    ep[8:11] = [499, 500, 501]
+    max_level = int(isg.max_terrain_level)
+    lv = rs.randint(0, max_level, size=n).astype(np.int64)
+    out = {}
+    hs = isg.height_samples.numpy()
+    meta = dict(name=name, n=n, steps=steps, seed=seed, rng_seed=0x5EED, terrain=terrain or {},
+                map_shape=list(hs.shape), map_sha256=hashlib.sha256(hs.tobytes()).hexdigest(),
+                max_terrain_level=max_level, border_size=float(isg.terrain.cfg.border_size),
+                num_cols=int(isg.cfg.terrain.num_cols), snap_kw=snap_kw or {}, map_seed=0,
+                zero_reset_step=ZERO_RESET_STEP if hook is not None else -1)
+    if store_map:
+        out["height_samples"] = hs.copy()
+    out["terrain_origins"] = isg.terrain_origins.numpy().copy()
+    out["terrain_types"] = isg.terrain_types.numpy().copy()
+    out["env_origins_init"] = isg.env_origins.numpy().copy()
+    out["ep_len_init"] = ep
+    out["levels_init"] = lv
+    rec, inp, rid = rh.run_a1(ns, env, seed=seed, steps=steps, ep_len_init=ep, levels_init=lv,
+                              snap_kw=snap_kw, snap_hook=hook)
+    for t, (r, i, ids) in enumerate(zip(rec, inp, rid)):
+        _pack(f"s{t}/in", i, out)
+        _pack(f"s{t}/out", r, out)
+        out[f"s{t}/reset_ids"] = ids[-1] if ids else np.zeros(0, dtype=np.int64)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    nres = [int(r["reset"].sum()) for r in rec]
+    print(f"{name}: {os.path.getsize(path) / 1e3:.0f} KB, resets per record {nres}")
+
+
+def gen_abb(ns, name, n, steps, seed):
+    env = rh.make_abb(ns, n)
+    rs = np.random.RandomState(seed)
+    ep = rs.randint(0, 190, size=n).astype(np.int64)
+    ep[:3] = [199, 200, 201]
+    out = dict(ep_len_init=ep)
+    rec, inp, rid = rh.run_abb(ns, env, seed=seed, steps=steps, ep_len_init=ep)
+    for t, (r, i, ids) in enumerate(zip(rec, inp, rid), start=1):
+        _pack(f"s{t}/in", i, out)
+        _pack(f"s{t}/out", r, out)
+        out[f"s{t}/reset_ids"] = ids[-1] if ids else np.zeros(0, dtype=np.int64)
+    meta = dict(name=name, n=n, steps=steps, seed=seed, rng_seed=0x5EED)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1e3:.0f} KB, resets {[int(r['reset'].sum()) for r in rec]}")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = rh.load_reference()
+    gen_a1(ns, "a1_small", n=48, steps=6, terrain=SMALL_TERRAIN, seed=11, store_map=True,
+           hook=small_hook, snap_kw=dict(p_base=0.12))
+    gen_a1(ns, "a1_fullmap", n=40, steps=2, terrain=None, seed=12, store_map=False,
+           snap_kw=dict(p_base=0.1))
+    gen_abb(ns, "abb_small", n=48, steps=4, seed=13)
+
+
+if __name__ == "__main__":
+    main()
