@@ -1,0 +1,64 @@
+"""In-tree build of ``libshifu_b200.so`` (nvcc, sm_100a only).
+
+    python -m shifu_b200.build            # (re)build when sources are newer than the .so
+
+nvcc cross-compiles without a GPU, so this also runs in the CPU-only build container.  The built
+library stays inside the package directory (git-ignored) so that it travels with the repo snapshot
+to the GPU box and is visible to the driver's "which .so got loaded" check.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+LIB_PATH = os.path.join(PKG_DIR, "libshifu_b200.so")
+
+SOURCES = ["capi.cu"]
+DEPS = ["capi.cu", "a1_kernels.cuh", "abb_kernels.cuh", "common_kernels.cuh", "exact_math.cuh", "philox.cuh"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--fmad=false",                    # no implicit FMA contraction: see csrc/exact_math.cuh
+    "-Xcompiler", "-fPIC", "-shared",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libshifu_b200.so cannot be built (there is no CPU fallback)")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.join(INCLUDE, "shifu_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    log = res.stdout + res.stderr
+    with open(os.path.join(PKG_DIR, "csrc", "ptxas.log"), "w") as f:
+        f.write(log)
+    if verbose:
+        print(log)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

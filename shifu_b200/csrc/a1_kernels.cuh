@@ -1,0 +1,627 @@
+// A1 conditional-walking kernels (sm_100a).  Rows a2, a3, a5-a7, a9-a14 of SURVEY.md §8(a).
+//
+// Everything here is HBM-/LSU-bound fp32 + integer work; there is no contraction, so no
+// tensor-core path.  The design rules that matter: one pass over every state tensor with
+// coalesced 128-bit loads, the obs row written once with streaming stores, grids sized by the
+// SM count, and the 187-point height scan served from an L2-resident tiled table.
+#pragma once
+#include "exact_math.cuh"
+#include "philox.cuh"
+#include "../../include/shifu_b200.h"
+
+namespace shifu {
+
+// Compile-time shape of the A1 task (validated against the descriptor in shifu_ctx_create).
+constexpr int A1_DOF = 12, A1_BODIES = 17, A1_HIST = 3, A1_OBS = 259;
+constexpr int A1_NX = 17, A1_NY = 11, A1_POINTS = A1_NX * A1_NY;   // 187
+constexpr int A1_HEAD = A1_OBS - A1_POINTS;                          // 72 non-height obs columns
+constexpr int A1_TILE = 32;       // envs per CTA
+constexpr int A1_THREADS = 192;   // 6 warps: 187 scan points + 5 idle lanes
+constexpr int TILE_SHIFT = 3;     // scan table stored in 8x8-cell tiles (128 B each)
+
+// Kernel-side constants (passed by value as a __grid_constant__ parameter: constant bank).
+struct A1K {
+  int n;
+  long long env_offset;
+  unsigned long long seed;
+  int base_body, n_leg, leg[SHIFU_MAX_LEG_BODIES], force_body;
+  int root_stride, root_offset;
+  float q0[A1_DOF], kp[A1_DOF], kd[A1_DOF], tau_max[A1_DOF];
+  float action_scale, clip_actions, clip_obs;
+  float px[A1_NX], py[A1_NY];
+  float border;
+  ConstDiv hdiv;          // horizontal_scale and its rounded reciprocal
+  int exact_div;          // 1: use __fdiv_rn instead of the 3-op constant division
+  float vscale, h_off, h_clip;
+  long long max_len;
+  float max_len_s, contact_thr;
+  float root0[7];
+  float xy_span, xy_low, force_span, force_low, cmd_span[3], cmd_low[3];
+  int curriculum, max_level, n_types;
+  float up_dist, down_factor;
+  int n_terms, terms[SHIFU_MAX_REWARD_TERMS];
+  float rp[SHIFU_MAX_REWARD_TERMS][2];
+  // scan table
+  const short* table;     // tiled min-of-3 table
+  int trows, tcols;       // valid index range: px in [0, trows-1], py in [0, tcols-1]
+  int tiles_y;            // tiles per table row
+  int tiled;              // 1: 8x8 tiles, 0: row-major (pitch = tcols)
+  double* stats;          // SHIFU_NUM_STATS accumulators
+};
+
+__device__ __forceinline__ float hdivide(float x, const A1K& k) {
+  return k.exact_div ? div_rn(x, k.hdiv.d) : div_const(x, k.hdiv);
+}
+
+__device__ __forceinline__ int table_index(unsigned px, unsigned py, const A1K& k) {
+  if (k.tiled) {
+    const unsigned tile = (px >> TILE_SHIFT) * (unsigned)k.tiles_y + (py >> TILE_SHIFT);
+    return (int)((tile << (2 * TILE_SHIFT)) | ((px & 7u) << TILE_SHIFT) | (py & 7u));
+  }
+  return (int)(px * (unsigned)k.tcols + py);
+}
+
+// ------------------------------------------------------------------------------------------
+// Scan-table build: T[px][py] = min(H[px][py], H[px+1][py], H[px][py+1])
+// (shifu/gym/isaac_gym.py:427-431 folded; the map is static after create_ground()).
+// ------------------------------------------------------------------------------------------
+__global__ void build_scan_table_kernel(const short* __restrict__ H, int rows, int cols,
+                                        short* __restrict__ T, int tiles_y, int tiled) {
+  const int trows = rows - 1, tcols = cols - 1;
+  const long long total = (long long)trows * tcols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i / tcols), py = (int)(i % tcols);
+    const short a = H[(long long)px * cols + py];
+    const short b = H[(long long)(px + 1) * cols + py];
+    const short c = H[(long long)px * cols + py + 1];
+    const short m = min(min(a, b), c);
+    long long o;
+    if (tiled) {
+      const long long tile = (long long)(px >> TILE_SHIFT) * tiles_y + (py >> TILE_SHIFT);
+      o = (tile << (2 * TILE_SHIFT)) | ((px & 7) << TILE_SHIFT) | (py & 7);
+    } else {
+      o = (long long)px * tcols + py;
+    }
+    T[o] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row a1/a2: (optional) action scale+clip, then one PD substep.
+//   tau = clip(kp*((a + q0) - q) - kd*qd, +-tau_max)       a1_conditional.py:66-67
+// One thread per (env, dof) pair; dof_state is read as float2 (pos, vel) — fully coalesced.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pd_torque_kernel(const __grid_constant__ A1K k, const float* __restrict__ a_in, float* __restrict__ a_out,
+                 const float2* __restrict__ dof, float* __restrict__ tau) {
+  const long long total = (long long)k.n * A1_DOF;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % A1_DOF);
+    float a = a_in[i];
+    if (a_out != nullptr) {
+      a = clampf(mul_rn(a, k.action_scale), -k.clip_actions, k.clip_actions);
+      a_out[i] = a;
+    }
+    const float2 s = dof[i];
+    const float e = sub_rn(add_rn(a, k.q0[d]), s.x);
+    const float t = sub_rn(mul_rn(k.kp[d], e), mul_rn(k.kd[d], s.y));
+    tau[i] = clampf(t, -k.tau_max[d], k.tau_max[d]);
+  }
+}
+
+// quat_rotate_inverse (isaacgym.torch_utils): a = v(2w^2-1); b = 2w(q x v); c = 2q(q.v); a - b + c
+__device__ __forceinline__ void rotate_inverse(const float* q, float vx, float vy, float vz, float* out) {
+  const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+  const float s = sub_rn(mul_rn(2.0f, mul_rn(qw, qw)), 1.0f);
+  const float cx = fma_rn(qy, vz, -mul_rn(qz, vy));   // torch CPU cross uses fma(a,b,-fl(c*d))
+  const float cy = fma_rn(qz, vx, -mul_rn(qx, vz));
+  const float cz = fma_rn(qx, vy, -mul_rn(qy, vx));
+  const float dot = add_rn(add_rn(mul_rn(qx, vx), mul_rn(qy, vy)), mul_rn(qz, vz));
+  const float v[3] = {vx, vy, vz}, c[3] = {cx, cy, cz}, qq[3] = {qx, qy, qz};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a = mul_rn(v[i], s);
+    const float b = mul_rn(mul_rn(c[i], qw), 2.0f);
+    const float cc = mul_rn(mul_rn(qq[i], dot), 2.0f);
+    out[i] = add_rn(sub_rn(a, b), cc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row a3: LeggedRobot.post_step (shifu/units/robot.py:222-229), one thread per env.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+body_frame_kernel(const __grid_constant__ A1K k, const float* __restrict__ root, float* __restrict__ lin,
+                  float* __restrict__ ang, float* __restrict__ pg, float* __restrict__ gvec) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k.n; e += gridDim.x * blockDim.x) {
+    const float* r = root + ((long long)e * k.root_stride + k.root_offset) * 13;
+    float row[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) row[j] = r[j];
+    float o[3];
+    rotate_inverse(row + 3, row[7], row[8], row[9], o);
+    lin[e * 3 + 0] = o[0]; lin[e * 3 + 1] = o[1]; lin[e * 3 + 2] = o[2];
+    rotate_inverse(row + 3, row[10], row[11], row[12], o);
+    ang[e * 3 + 0] = o[0]; ang[e * 3 + 1] = o[1]; ang[e * 3 + 2] = o[2];
+    rotate_inverse(row + 3, 0.0f, 0.0f, -1.0f, o);
+    pg[e * 3 + 0] = o[0]; pg[e * 3 + 1] = o[1]; pg[e * 3 + 2] = o[2];
+    if (gvec != nullptr) { gvec[e * 3 + 0] = 0.0f; gvec[e * 3 + 1] = 0.0f; gvec[e * 3 + 2] = -1.0f; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The height scan of ONE point (rows a5): yaw-rotate (bx,by), translate, to cell index, gather.
+//   quat_apply_yaw: shifu/utils/terrain.py:202-206; get_heights: shifu/gym/isaac_gym.py:416-433
+// ev = {2*zq, zq, wq, pos_x, pos_y} with (zq, wq) the normalised yaw quaternion.
+// Every op keeps the rounding of the aten elementwise op it stands for.
+// ------------------------------------------------------------------------------------------
+struct ScanEnv {
+  float z2, z, w, x, y;
+};
+
+__device__ __forceinline__ ScanEnv make_scan_env(const float* root_row) {
+  const float qz = root_row[5], qw = root_row[6];
+  // normalize((0,0,qz,qw)): x / clamp(sqrt(fl(qz^2)+fl(qw^2)), 1e-9)
+  float nrm = sqrt_rn(add_rn(mul_rn(qz, qz), mul_rn(qw, qw)));
+  nrm = fmaxf(nrm, 1e-9f);
+  ScanEnv ev;
+  ev.z = div_rn(qz, nrm);
+  ev.w = div_rn(qw, nrm);
+  ev.z2 = mul_rn(ev.z, 2.0f);
+  ev.x = root_row[0];
+  ev.y = root_row[1];
+  return ev;
+}
+
+__device__ __forceinline__ float scan_point(const ScanEnv& ev, float bx, float by, const A1K& k,
+                                            unsigned* opx, unsigned* opy) {
+  // t = 2*(q_xyz x b) with q_xyz = (0,0,z), b = (bx,by,0)  ->  (-2z*by, 2z*bx, 0)
+  const float tx = -mul_rn(ev.z2, by);
+  const float ty = mul_rn(ev.z2, bx);
+  // b + w*t + q_xyz x t ;  q_xyz x t = (-z*ty, z*tx, 0)
+  const float rx = add_rn(add_rn(bx, mul_rn(ev.w, tx)), -mul_rn(ev.z, ty));
+  const float ry = add_rn(add_rn(by, mul_rn(ev.w, ty)), mul_rn(ev.z, tx));
+  // + base xy, + border, / horizontal_scale, .long() (trunc), clip to [0, dim-2]
+  const float fx = hdivide(add_rn(add_rn(rx, ev.x), k.border), k);
+  const float fy = hdivide(add_rn(add_rn(ry, ev.y), k.border), k);
+  // float->unsigned conversion truncates toward zero and saturates (negatives -> 0)
+  const unsigned px = min(__float2uint_rz(fx), (unsigned)(k.trows - 1));
+  const unsigned py = min(__float2uint_rz(fy), (unsigned)(k.tcols - 1));
+  *opx = px; *opy = py;
+  const short h = __ldg(k.table + table_index(px, py, k));
+  return mul_rn((float)h, k.vscale);
+}
+
+// Stand-alone get_heights (for user-hook tasks and the index parity tests): one CTA per
+// A1_TILE envs, thread t < 187 owns scan point t.
+__global__ void __launch_bounds__(A1_THREADS)
+get_heights_kernel(const __grid_constant__ A1K k, const float* __restrict__ root, float* __restrict__ mh,
+                   int* __restrict__ cell_idx) {
+  __shared__ ScanEnv s_ev[A1_TILE];
+  const int t = threadIdx.x;
+  const float bx = k.px[t % A1_NX], by = k.py[(t / A1_NX) % A1_NY];
+  for (int e0 = blockIdx.x * A1_TILE; e0 < k.n; e0 += gridDim.x * A1_TILE) {
+    const int ne = min(A1_TILE, k.n - e0);
+    __syncthreads();
+    if (t < ne) s_ev[t] = make_scan_env(root + ((long long)(e0 + t) * k.root_stride + k.root_offset) * 13);
+    __syncthreads();
+    if (t < A1_POINTS) {
+      for (int e = 0; e < ne; ++e) {
+        unsigned px, py;
+        const float h = scan_point(s_ev[e], bx, by, k, &px, &py);
+        const long long o = (long long)(e0 + e) * A1_POINTS + t;
+        mh[o] = h;
+        if (cell_idx != nullptr) { cell_idx[2 * o] = (int)px; cell_idx[2 * o + 1] = (int)py; }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reset of ONE env (rows a9-a11): A1Conditional.reset_idx, a1_conditional.py:116-120, i.e.
+// update_terrain_curriculum (:204-221) -> ShifuVecEnv.reset_idx (env.py:114-130) ->
+// IsaacGymEnv.reset_idx / A1Robot.reset_idx (isaac_gym.py:54-73, robot.py:74-86,
+// a1_conditional.py:43-50,77-87) -> sample_command (:194-200).
+// root_row / dof_row / hist_row are the env's rows wherever the caller keeps them (shared memory
+// inside K-main, global memory in the stand-alone kernel); with MIRROR the root/dof rows are
+// additionally written through to the flat gym tensors.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool MIRROR>
+__device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& io, long long step, int ge,
+                                             float* root_row, float* dof_row, float* hist_row,
+                                             float (&cmd)[3], float (&esum)[SHIFU_MAX_REWARD_TERMS],
+                                             long long& len, double (&st_sum)[SHIFU_MAX_REWARD_TERMS],
+                                             long long& level_delta) {
+  const long long gid = k.env_offset + ge;
+  float ox = io.env_origins[ge * 3LL + 0], oy = io.env_origins[ge * 3LL + 1], oz = io.env_origins[ge * 3LL + 2];
+  if (k.curriculum) {                                                    // a1_conditional.py:204-221
+    const float dist = norm2_fma(sub_rn(root_row[0], ox), sub_rn(root_row[1], oy));
+    const bool up = dist > k.up_dist;
+    const float need = mul_rn(mul_rn(norm2_fma(cmd[0], cmd[1]), k.max_len_s), k.down_factor);
+    const bool down = (dist < need) && !up;
+    const long long old_level = io.terrain_levels[ge];
+    long long level = old_level + (up ? 1 : 0) - (down ? 1 : 0);
+    const long long rnd = randint(draw(k.seed, gid, step, STREAM_LEVEL).x, k.max_level);
+    level = (level >= k.max_level) ? rnd : (level < 0 ? 0 : level);
+    io.terrain_levels[ge] = level;
+    level_delta = level - old_level;
+    const long long ty = io.terrain_types[ge];                           // isaac_gym.py:387-391
+    const float* org = io.terrain_origins + (level * k.n_types + ty) * 3;
+    ox = org[0]; oy = org[1]; oz = org[2];
+    io.env_origins[ge * 3LL + 0] = ox; io.env_origins[ge * 3LL + 1] = oy; io.env_origins[ge * 3LL + 2] = oz;
+  }
+  // Robot._reset_dof_state, shifu/units/robot.py:74-77
+#pragma unroll
+  for (int d = 0; d < A1_DOF; ++d) {
+    dof_row[2 * d] = k.q0[d];
+    dof_row[2 * d + 1] = 0.0f;
+    io.dof_targets[ge * (long long)A1_DOF + d] = k.q0[d];
+  }
+  if (MIRROR) {
+    float4* drow = reinterpret_cast<float4*>(io.dof_state + (long long)ge * (A1_DOF * 2));
+    const float4* srow = reinterpret_cast<const float4*>(dof_row);
+#pragma unroll
+    for (int j = 0; j < A1_DOF * 2 / 4; ++j) drow[j] = srow[j];
+  }
+  // A1Robot._reset_root_state, a1_conditional.py:43-50
+  const U4 uxy = draw(k.seed, gid, step, STREAM_XY);
+  float rr[13];
+  rr[0] = add_rn(add_rn(k.root0[0], ox), add_rn(mul_rn(k.xy_span, u01(uxy.x)), k.xy_low));
+  rr[1] = add_rn(add_rn(k.root0[1], oy), add_rn(mul_rn(k.xy_span, u01(uxy.y)), k.xy_low));
+  rr[2] = add_rn(k.root0[2], oz);
+  rr[3] = k.root0[3]; rr[4] = k.root0[4]; rr[5] = k.root0[5]; rr[6] = k.root0[6];
+#pragma unroll
+  for (int j = 7; j < 13; ++j) rr[j] = 0.0f;
+  float* grow = io.root_state + ((long long)ge * k.root_stride + k.root_offset) * 13;
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    root_row[j] = rr[j];
+    if (MIRROR) grow[j] = rr[j];
+  }
+  // update_rand_force_buf, a1_conditional.py:82-87
+  const U4 uf = draw(k.seed, gid, step, STREAM_FORCE);
+  float* fr = io.rand_force + ((long long)ge * A1_BODIES + k.force_body) * 3;
+  fr[0] = add_rn(mul_rn(k.force_span, u01(uf.x)), k.force_low);
+  fr[1] = add_rn(mul_rn(k.force_span, u01(uf.y)), k.force_low);
+  fr[2] = add_rn(mul_rn(k.force_span, u01(uf.z)), k.force_low);
+  // ShifuVecEnv.reset_idx, env.py:119-122 ; log_info, env.py:149-153
+  len = 0;
+#pragma unroll
+  for (int j = 0; j < A1_DOF * A1_HIST; ++j) hist_row[j] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
+    if (j < k.n_terms) { st_sum[j] = (double)esum[j]; esum[j] = 0.0f; }
+  }
+  // sample_command, a1_conditional.py:194-200
+  const U4 uc = draw(k.seed, gid, step, STREAM_CMD);
+  cmd[0] = add_rn(mul_rn(k.cmd_span[0], u01(uc.x)), k.cmd_low[0]);
+  cmd[1] = add_rn(mul_rn(k.cmd_span[1], u01(uc.y)), k.cmd_low[1]);
+  cmd[2] = add_rn(mul_rn(k.cmd_span[2], u01(uc.z)), k.cmd_low[2]);
+  io.command[ge * 3LL + 0] = cmd[0]; io.command[ge * 3LL + 1] = cmd[1]; io.command[ge * 3LL + 2] = cmd[2];
+}
+
+// Warp-level reduction of the per-step log sums (env.py:149-153) -> one set of atomics per warp.
+__device__ __forceinline__ void a1_log_sums(const A1K& k, bool reset, const double (&st_sum)[SHIFU_MAX_REWARD_TERMS],
+                                            long long level_delta, int lane) {
+  const unsigned any = __ballot_sync(0xffffffffu, reset);
+  if (!any) return;
+  const double cnt = warp_sum(reset ? 1.0 : 0.0);
+  const double dl = warp_sum((double)level_delta);
+#pragma unroll
+  for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
+    if (j < k.n_terms) {
+      const double v = warp_sum(st_sum[j]);
+      if (lane == 0) atomicAdd(k.stats + SHIFU_STAT_TERM0 + j, v);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(k.stats + SHIFU_STAT_NRESET, cnt);
+    if (dl != 0.0) atomicAdd(k.stats + SHIFU_STAT_LEVEL_SUM, dl);
+  }
+}
+
+// Stand-alone reset_idx(env_ids) (user calls / ShifuVecEnv.reset, env.py:108-112): one thread per id;
+// ids == nullptr means arange(n_ids).
+__global__ void __launch_bounds__(128)
+a1_reset_idx_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io,
+                    const long long* __restrict__ ids, int n_ids) {
+  const long long step = (io.step_dev != nullptr) ? *io.step_dev : io.step;
+  const int lane = threadIdx.x & 31;
+  for (int i0 = blockIdx.x * blockDim.x; i0 < n_ids; i0 += gridDim.x * blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    bool reset = false;
+    double st_sum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+    for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) st_sum[j] = 0.0;
+    long long level_delta = 0;
+    if (i < n_ids) {
+      const int ge = (ids != nullptr) ? (int)ids[i] : i;
+      if (ge >= 0 && ge < k.n) {
+        reset = true;
+        float cmd[3], esum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cmd[j] = io.command[ge * 3LL + j];
+#pragma unroll
+        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) esum[j] = (j < k.n_terms) ? io.ep_sums[j][ge] : 0.0f;
+        long long len = 0;
+        a1_reset_env<false>(k, io, step, ge, io.root_state + ((long long)ge * k.root_stride + k.root_offset) * 13,
+                            io.dof_state + (long long)ge * (A1_DOF * 2),
+                            io.history + (long long)ge * (A1_DOF * A1_HIST), cmd, esum, len, st_sum, level_delta);
+        io.ep_len[ge] = 0;
+        io.reset_buf[ge] = 1;
+#pragma unroll
+        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j)
+          if (j < k.n_terms) io.ep_sums[j][ge] = 0.0f;
+      }
+    }
+    a1_log_sums(k, reset, st_sum, level_delta, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-main: the fused post-physics step (ShifuVecEnv.post_step, shifu/gym/env.py:93-106, with the
+// A1 hooks, + obs clip env.py:90).  One CTA = A1_TILE consecutive envs, four phases:
+//   A  coalesced 128-bit loads of the tile's root/dof/contact/history/torque/action rows -> smem
+//   B  warp 0, one lane per env: ep_len, termination, reward terms + episode sums, reset
+//      (curriculum, Philox draws, state rewrite, log sums), obs head (72 cols), history push,
+//      carried body-frame velocities
+//   C  all warps, thread t owns scan point t: 187-point height scan per env, obs cols 72..258
+//      streamed straight to HBM (each warp writes 128 contiguous bytes)
+//   D  coalesced write-back of the obs head and the history tile
+// ------------------------------------------------------------------------------------------
+struct A1Smem {
+  float root[A1_TILE][13];
+  float dof[A1_TILE][A1_DOF * 2];
+  float contact[A1_TILE][A1_BODIES * 3];
+  float hist[A1_TILE][A1_DOF * A1_HIST];
+  float tau[A1_TILE][A1_DOF];
+  float act[A1_TILE][A1_DOF];
+  float head[A1_TILE][A1_HEAD];
+  ScanEnv ev[A1_TILE];
+  float zb[A1_TILE];
+};
+
+// Copy `n` floats global -> shared with float4 when both sides are 16-byte aligned.
+__device__ __forceinline__ void load_span(float* __restrict__ dst, const float* __restrict__ src, int n,
+                                          int tid, int nthreads) {
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+    const int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = tid; i < n4; i += nthreads) d4[i] = __ldg(s4 + i);
+    for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
+  }
+}
+
+__device__ __forceinline__ void store_span(float* __restrict__ dst, const float* __restrict__ src, int n,
+                                           int tid, int nthreads) {
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+    const int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = tid; i < n4; i += nthreads) d4[i] = s4[i];
+    for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
+  }
+}
+
+__global__ void __launch_bounds__(A1_THREADS)
+a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  A1Smem& s = *reinterpret_cast<A1Smem*>(smem_raw);
+  const int t = threadIdx.x;
+  const long long step = (io.step_dev != nullptr) ? *io.step_dev : io.step;
+  // scan point owned by this thread (thread 187..191 idle in phase C)
+  const float bx = k.px[t % A1_NX], by = k.py[(t / A1_NX) % A1_NY];
+
+  for (int e0 = blockIdx.x * A1_TILE; e0 < k.n; e0 += gridDim.x * A1_TILE) {
+    const int ne = min(A1_TILE, k.n - e0);
+    const int ge = e0 + t;                 // env of this lane in phase B
+    const bool lane_env = (t < ne);
+
+    // ---- prefetch the per-env scalars warp 0 needs in phase B (in flight during phase A) ----
+    long long len = 0;
+    float cmd[3] = {0, 0, 0}, lin[3] = {0, 0, 0}, ang[3] = {0, 0, 0};
+    float esum[SHIFU_MAX_REWARD_TERMS];
+    if (lane_env) {
+      len = io.ep_len[ge];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        cmd[j] = io.command[ge * 3LL + j];
+        lin[j] = io.base_lin_vel[ge * 3LL + j];
+        ang[j] = io.base_ang_vel[ge * 3LL + j];
+      }
+#pragma unroll
+      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) esum[j] = (j < k.n_terms) ? io.ep_sums[j][ge] : 0.0f;
+    }
+
+    // ---- phase A ----
+    if (k.root_stride == 1 && k.root_offset == 0) {
+      load_span(&s.root[0][0], io.root_state + (long long)e0 * 13, ne * 13, t, A1_THREADS);
+    } else {
+      for (int i = t; i < ne * 13; i += A1_THREADS) {
+        const int e = i / 13, c = i % 13;
+        s.root[e][c] = io.root_state[((long long)(e0 + e) * k.root_stride + k.root_offset) * 13 + c];
+      }
+    }
+    load_span(&s.dof[0][0], io.dof_state + (long long)e0 * (A1_DOF * 2), ne * A1_DOF * 2, t, A1_THREADS);
+    load_span(&s.contact[0][0], io.contact_state + (long long)e0 * (A1_BODIES * 3), ne * A1_BODIES * 3, t,
+              A1_THREADS);
+    load_span(&s.hist[0][0], io.history + (long long)e0 * (A1_DOF * A1_HIST), ne * A1_DOF * A1_HIST, t,
+              A1_THREADS);
+    load_span(&s.tau[0][0], io.torques + (long long)e0 * A1_DOF, ne * A1_DOF, t, A1_THREADS);
+    load_span(&s.act[0][0], io.actions + (long long)e0 * A1_DOF, ne * A1_DOF, t, A1_THREADS);
+    __syncthreads();
+
+    // ---- phase B ----
+    if (t < 32) {
+      bool reset = false;
+      double st_sum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) st_sum[j] = 0.0;
+      long long level_delta = 0;
+      if (lane_env) {
+        const int e = t;
+        // heights are measured at the PRE-reset pose (isaac_gym.py:320-322 runs before post_step)
+        s.ev[e] = make_scan_env(s.root[e]);
+        len += 1;                                                          // env.py:95
+        // -- termination, a1_conditional.py:146-150
+        const float* fb = &s.contact[e][k.base_body * 3];
+        const bool contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
+        const bool time_out = len > k.max_len;
+        reset = contact_term | time_out;
+        // -- reward terms in list order, env.py:180-185
+        float rew = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
+          if (j < k.n_terms) {
+            const float p0 = k.rp[j][0], p1 = k.rp[j][1];
+            float r = 0.0f;
+            switch (k.terms[j]) {
+              case SHIFU_REW_TRACKING_LIN_VEL: {
+                const float dx = sub_rn(cmd[0], lin[0]), dy = sub_rn(cmd[1], lin[1]);
+                const float err = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+                r = mul_rn(p0, expf(div_rn(-err, p1)));
+              } break;
+              case SHIFU_REW_TRACKING_ANG_VEL: {
+                const float d = sub_rn(cmd[2], ang[2]);
+                r = mul_rn(p0, expf(div_rn(-mul_rn(d, d), p1)));
+              } break;
+              case SHIFU_REW_STABILIZING_BASE: {
+                const float zv = mul_rn(p0, mul_rn(lin[2], lin[2]));
+                const float av = mul_rn(p1, add_rn(mul_rn(ang[0], ang[0]), mul_rn(ang[1], ang[1])));
+                r = add_rn(zv, av);
+              } break;
+              case SHIFU_REW_SMOOTHING_ACTION: {
+                float f1 = 0.0f, f2 = 0.0f;
+#pragma unroll
+                for (int d = 0; d < A1_DOF; ++d) {
+                  const float a0 = s.hist[e][d * A1_HIST + 0], a1 = s.hist[e][d * A1_HIST + 1],
+                              a2 = s.hist[e][d * A1_HIST + 2];
+                  const float d1 = sub_rn(a1, a0);
+                  const float d2 = add_rn(sub_rn(a2, mul_rn(2.0f, a1)), a0);
+                  f1 = add_rn(f1, mul_rn(d1, d1));
+                  f2 = add_rn(f2, mul_rn(d2, d2));
+                }
+                r = mul_rn(p0, add_rn(f1, f2));
+              } break;
+              case SHIFU_REW_LEG_COLLISION: {
+                int cnt = 0;
+                for (int b = 0; b < k.n_leg; ++b) {
+                  const float* f = &s.contact[e][k.leg[b] * 3];
+                  cnt += (norm3_fma(f[0], f[1], f[2]) > p1) ? 1 : 0;
+                }
+                r = mul_rn(p0, (float)cnt);
+              } break;
+              case SHIFU_REW_TORQUES: {
+                float acc = 0.0f;
+#pragma unroll
+                for (int d = 0; d < A1_DOF; ++d) acc = add_rn(acc, mul_rn(s.tau[e][d], s.tau[e][d]));
+                r = mul_rn(p0, acc);
+              } break;
+              default: break;
+            }
+            esum[j] = add_rn(esum[j], r);
+            rew = add_rn(rew, r);
+          }
+        }
+        io.rew_buf[ge] = rew;
+        io.reset_buf[ge] = reset ? 1 : 0;
+        io.time_out_buf[ge] = time_out ? 1 : 0;
+        io.contact_term_buf[ge] = contact_term ? 1 : 0;
+
+        // -- reset (env.py:101-102 -> a1_conditional.py:116-120)
+        if (reset)
+          a1_reset_env<true>(k, io, step, ge, s.root[e], s.dof[e], s.hist[e], cmd, esum, len, st_sum,
+                             level_delta);
+        io.ep_len[ge] = len;
+#pragma unroll
+        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j)
+          if (j < k.n_terms) io.ep_sums[j][ge] = esum[j];
+
+        // -- observation head, a1_conditional.py:131-144 (post-reset command/dof/history, D8)
+        float* h = s.head[e];
+        const float c = k.clip_obs;
+        h[0] = clampf(cmd[0], -c, c); h[1] = clampf(cmd[1], -c, c); h[2] = clampf(cmd[2], -c, c);
+        h[3] = clampf(lin[0], -c, c); h[4] = clampf(lin[1], -c, c); h[5] = clampf(lin[2], -c, c);
+        h[6] = clampf(ang[0], -c, c); h[7] = clampf(ang[1], -c, c); h[8] = clampf(ang[2], -c, c);
+        h[9] = 0.0f; h[10] = 0.0f; h[11] = clampf(-1.0f, -c, c);          // gravity_vec, robot.py:223
+#pragma unroll
+        for (int d = 0; d < A1_DOF; ++d) {
+          h[12 + d] = clampf(sub_rn(s.dof[e][2 * d], k.q0[d]), -c, c);
+          h[24 + d] = clampf(s.dof[e][2 * d + 1], -c, c);
+        }
+        // HistoryRecorder.flatten (train.py:33-35): slot-major; then add() (train.py:12-14)
+#pragma unroll
+        for (int d = 0; d < A1_DOF; ++d) {
+          const float a0 = s.hist[e][d * A1_HIST + 0], a1 = s.hist[e][d * A1_HIST + 1],
+                      a2 = s.hist[e][d * A1_HIST + 2];
+          h[36 + d] = clampf(a0, -c, c);
+          h[48 + d] = clampf(a1, -c, c);
+          h[60 + d] = clampf(a2, -c, c);
+          s.hist[e][d * A1_HIST + 2] = a1;
+          s.hist[e][d * A1_HIST + 1] = a0;
+          s.hist[e][d * A1_HIST + 0] = s.act[e][d];
+        }
+        s.zb[e] = sub_rn(s.root[e][2], k.h_off);                          // post-reset base z
+        // -- carried body-frame velocities for the next control step (robot.py:222-229, D7)
+        if (io.carry_body_frame) {
+          float o[3];
+          rotate_inverse(&s.root[e][3], s.root[e][7], s.root[e][8], s.root[e][9], o);
+          io.base_lin_vel[ge * 3LL + 0] = o[0]; io.base_lin_vel[ge * 3LL + 1] = o[1];
+          io.base_lin_vel[ge * 3LL + 2] = o[2];
+          rotate_inverse(&s.root[e][3], s.root[e][10], s.root[e][11], s.root[e][12], o);
+          io.base_ang_vel[ge * 3LL + 0] = o[0]; io.base_ang_vel[ge * 3LL + 1] = o[1];
+          io.base_ang_vel[ge * 3LL + 2] = o[2];
+          rotate_inverse(&s.root[e][3], 0.0f, 0.0f, -1.0f, o);
+          io.projected_gravity[ge * 3LL + 0] = o[0]; io.projected_gravity[ge * 3LL + 1] = o[1];
+          io.projected_gravity[ge * 3LL + 2] = o[2];
+        }
+      }
+      a1_log_sums(k, reset, st_sum, level_delta, t);
+    }
+    __syncthreads();
+
+    // ---- phase C: 187-point scan; obs[., 72 + t] = clip((z - 0.5) - h, +-1) ----
+    if (t < A1_POINTS) {
+      float* orow = io.obs_buf + (long long)e0 * A1_OBS + A1_HEAD + t;
+      float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + (long long)e0 * A1_POINTS + t
+                                                     : nullptr;
+#pragma unroll 4
+      for (int e = 0; e < ne; ++e) {
+        unsigned px, py;
+        const float hgt = scan_point(s.ev[e], bx, by, k, &px, &py);
+        float v = clampf(sub_rn(s.zb[e], hgt), -k.h_clip, k.h_clip);
+        v = clampf(v, -k.clip_obs, k.clip_obs);
+        __stcs(orow + (long long)e * A1_OBS, v);
+        if (mrow != nullptr) __stcs(mrow + (long long)e * A1_POINTS, hgt);
+      }
+    }
+
+    // ---- phase D: obs head + history tile ----
+    {
+      float* obase = io.obs_buf + (long long)e0 * A1_OBS;
+      const float* hsrc = &s.head[0][0];
+      for (int i = t; i < ne * A1_HEAD; i += A1_THREADS) {
+        const int e = i / A1_HEAD, j = i - e * A1_HEAD;
+        __stcs(obase + (long long)e * A1_OBS + j, hsrc[i]);
+      }
+      store_span(io.history + (long long)e0 * (A1_DOF * A1_HIST), &s.hist[0][0], ne * A1_DOF * A1_HIST, t,
+                 A1_THREADS);
+    }
+    __syncthreads();   // smem is reused by the next tile of a grid-stride CTA
+  }
+}
+
+}  // namespace shifu

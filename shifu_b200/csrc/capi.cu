@@ -1,0 +1,376 @@
+// C-ABI entry points of libshifu_b200.so (see include/shifu_b200.h for the contract).
+// Host side only validates arguments, fills the kernel constant blocks and enqueues launches
+// on the caller's stream.  nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <new>
+
+#include "../../include/shifu_b200.h"
+#include "a1_kernels.cuh"
+#include "abb_kernels.cuh"
+#include "common_kernels.cuh"
+
+using namespace shifu;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail((int)_e, "%s: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+#define REQUIRE_PTR(p)                                                      \
+  do {                                                                      \
+    if ((p) == nullptr) return fail(SHIFU_E_NULL, "%s is NULL", #p);        \
+  } while (0)
+
+#define REQUIRE_ALIGNED(p, a)                                                                    \
+  do {                                                                                           \
+    if ((reinterpret_cast<uintptr_t>(p) & ((a) - 1)) != 0)                                       \
+      return fail(SHIFU_E_ALIGN, "%s must be %d-byte aligned", #p, (int)(a));                    \
+  } while (0)
+
+struct ShifuCtx {
+  int device = 0;
+  int sm_count = 0;
+  bool is_a1 = false, is_abb = false;
+  ShifuA1Desc a1{};
+  ShifuAbbDesc abb{};
+  A1K a1k{};
+  AbbK abbk{};
+  short* d_table = nullptr;
+  double* d_stats = nullptr;         // SHIFU_NUM_STATS accumulators + [SHIFU_NUM_STATS] = level sum
+  unsigned long long* d_chain = nullptr;
+  unsigned* d_ticket = nullptr;      // [0] ticket, [1] retired CTAs
+  int chain_len = 0;
+  unsigned epoch = 0;
+  int a1_grid = 0;
+};
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" const char* shifu_last_error(void) { return g_err; }
+extern "C" int shifu_abi_version(void) { return SHIFU_ABI_VERSION; }
+
+static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
+  if (d.abi_version != SHIFU_ABI_VERSION) return fail(SHIFU_E_RANGE, "ShifuA1Desc.abi_version %d != %d", d.abi_version, SHIFU_ABI_VERSION);
+  if (d.num_envs <= 0) return fail(SHIFU_E_RANGE, "num_envs must be > 0 (got %d)", d.num_envs);
+  if (d.num_dof != A1_DOF || d.num_bodies != A1_BODIES || d.num_hist != A1_HIST || d.num_obs != A1_OBS ||
+      d.num_points_x != A1_NX || d.num_points_y != A1_NY)
+    return fail(SHIFU_E_RANGE,
+                "this build is specialised for dof=%d bodies=%d hist=%d obs=%d grid=%dx%d (got %d %d %d %d %dx%d)",
+                A1_DOF, A1_BODIES, A1_HIST, A1_OBS, A1_NX, A1_NY, d.num_dof, d.num_bodies, d.num_hist, d.num_obs,
+                d.num_points_x, d.num_points_y);
+  if (d.base_body < 0 || d.base_body >= A1_BODIES || d.force_body < 0 || d.force_body >= A1_BODIES)
+    return fail(SHIFU_E_RANGE, "base_body/force_body out of range");
+  if (d.num_leg_bodies < 0 || d.num_leg_bodies > SHIFU_MAX_LEG_BODIES) return fail(SHIFU_E_RANGE, "num_leg_bodies out of range");
+  for (int i = 0; i < d.num_leg_bodies; ++i)
+    if (d.leg_bodies[i] < 0 || d.leg_bodies[i] >= A1_BODIES) return fail(SHIFU_E_RANGE, "leg_bodies[%d] out of range", i);
+  if (d.num_reward_terms < 0 || d.num_reward_terms > SHIFU_MAX_REWARD_TERMS) return fail(SHIFU_E_RANGE, "num_reward_terms out of range");
+  for (int i = 0; i < d.num_reward_terms; ++i)
+    if (d.reward_terms[i] < 0 || d.reward_terms[i] > SHIFU_REW_TORQUES)
+      return fail(SHIFU_E_RANGE, "reward_terms[%d]=%d is not an A1 term", i, d.reward_terms[i]);
+  if (d.root_stride < 1 || d.root_offset < 0 || d.root_offset >= d.root_stride) return fail(SHIFU_E_RANGE, "root_stride/root_offset invalid");
+  if (!(d.horizontal_scale > 0.f) || d.max_terrain_level < 1 || d.num_terrain_types < 1) return fail(SHIFU_E_RANGE, "terrain constants invalid");
+  std::memset(&k, 0, sizeof(k));
+  k.n = d.num_envs;
+  k.env_offset = d.env_offset;
+  k.seed = d.rng_seed;
+  k.base_body = d.base_body;
+  k.n_leg = d.num_leg_bodies;
+  for (int i = 0; i < d.num_leg_bodies; ++i) k.leg[i] = d.leg_bodies[i];
+  k.force_body = d.force_body;
+  k.root_stride = d.root_stride;
+  k.root_offset = d.root_offset;
+  for (int i = 0; i < A1_DOF; ++i) { k.q0[i] = d.q0[i]; k.kp[i] = d.kp[i]; k.kd[i] = d.kd[i]; k.tau_max[i] = d.torque_limit[i]; }
+  k.action_scale = d.action_scale; k.clip_actions = d.clip_actions; k.clip_obs = d.clip_obs;
+  for (int i = 0; i < A1_NX; ++i) k.px[i] = d.points_x[i];
+  for (int i = 0; i < A1_NY; ++i) k.py[i] = d.points_y[i];
+  k.border = d.border_size;
+  k.hdiv.d = d.horizontal_scale;
+  k.hdiv.r = 1.0f / d.horizontal_scale;
+  // The 3-op constant division is proven (exhaustively) for 0.1f only; anything else divides.
+  k.exact_div = (d.horizontal_scale == 0.1f) ? 0 : 1;
+  k.vscale = d.vertical_scale; k.h_off = d.height_offset; k.h_clip = d.height_clip;
+  k.max_len = d.max_episode_length; k.max_len_s = d.max_episode_length_s; k.contact_thr = d.contact_term_force;
+  for (int i = 0; i < 7; ++i) k.root0[i] = d.default_root[i];
+  // torch_rand_float(lo, hi): (hi - lo) * u + lo with (hi - lo) formed in Python double arithmetic
+  k.xy_span = (float)((double)d.reset_xy_range - (double)(-d.reset_xy_range)); k.xy_low = -d.reset_xy_range;
+  k.force_span = (float)((double)d.push_force_max - (double)(-d.push_force_max)); k.force_low = -d.push_force_max;
+  for (int i = 0; i < 3; ++i) { k.cmd_span[i] = (float)((double)d.cmd_high[i] - (double)d.cmd_low[i]); k.cmd_low[i] = d.cmd_low[i]; }
+  k.curriculum = d.curriculum; k.max_level = d.max_terrain_level; k.n_types = d.num_terrain_types;
+  k.up_dist = d.level_up_distance; k.down_factor = d.level_down_factor;
+  k.n_terms = d.num_reward_terms;
+  for (int i = 0; i < d.num_reward_terms; ++i) { k.terms[i] = d.reward_terms[i]; k.rp[i][0] = d.reward_params[i][0]; k.rp[i][1] = d.reward_params[i][1]; }
+  return SHIFU_OK;
+}
+
+static int fill_abbk(const ShifuAbbDesc& d, AbbK& k) {
+  if (d.abi_version != SHIFU_ABI_VERSION) return fail(SHIFU_E_RANGE, "ShifuAbbDesc.abi_version %d != %d", d.abi_version, SHIFU_ABI_VERSION);
+  if (d.num_envs <= 0) return fail(SHIFU_E_RANGE, "num_envs must be > 0 (got %d)", d.num_envs);
+  if (d.num_actors < 1 || d.num_bodies < 1 || d.num_dof < 0 || d.num_dof > SHIFU_MAX_DOF) return fail(SHIFU_E_RANGE, "actor/body/dof counts invalid");
+  const int acts[4] = {d.robot_actor, d.table_actor, d.cube_actor, d.goal_actor};
+  for (int i = 0; i < 4; ++i) if (acts[i] < 0 || acts[i] >= d.num_actors) return fail(SHIFU_E_RANGE, "actor index %d out of range", i);
+  if (d.ee_body < 0 || d.ee_body >= d.num_bodies) return fail(SHIFU_E_RANGE, "ee_body out of range");
+  if (d.num_reward_terms < 0 || d.num_reward_terms > SHIFU_MAX_REWARD_TERMS) return fail(SHIFU_E_RANGE, "num_reward_terms out of range");
+  for (int i = 0; i < d.num_reward_terms; ++i)
+    if (d.reward_terms[i] != SHIFU_REW_ABB_REACHING && d.reward_terms[i] != SHIFU_REW_ABB_SUCCESS)
+      return fail(SHIFU_E_RANGE, "reward_terms[%d]=%d is not an ABB term", i, d.reward_terms[i]);
+  std::memset(&k, 0, sizeof(k));
+  k.n = d.num_envs; k.env_offset = d.env_offset; k.seed = d.rng_seed;
+  k.n_actors = d.num_actors; k.n_bodies = d.num_bodies; k.n_dof = d.num_dof; k.ee_body = d.ee_body;
+  k.robot_actor = d.robot_actor; k.table_actor = d.table_actor; k.cube_actor = d.cube_actor; k.goal_actor = d.goal_actor;
+  for (int i = 0; i < 2; ++i) { k.min_xy[i] = d.min_ee_pos[i]; k.max_xy[i] = d.max_ee_pos[i]; }
+  for (int i = 0; i < d.num_dof; ++i) k.q0[i] = d.q0[i];
+  for (int i = 0; i < 7; ++i) { k.robot_root[i] = d.robot_root[i]; k.table_root[i] = d.table_root[i]; }
+  for (int i = 0; i < 3; ++i) { k.pos_low[i] = d.box_pos_low[i]; k.pos_high[i] = d.box_pos_high[i]; }
+  k.goal_z = d.goal_z; k.success_dist = d.success_distance;
+  k.max_len = d.max_episode_length; k.max_len_s = d.max_episode_length_s; k.clip_obs = d.clip_obs;
+  k.n_terms = d.num_reward_terms;
+  for (int i = 0; i < d.num_reward_terms; ++i) { k.terms[i] = d.reward_terms[i]; k.rp[i][0] = d.reward_params[i][0]; k.rp[i][1] = d.reward_params[i][1]; }
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_ctx_create(int device, const ShifuA1Desc* a1, const ShifuAbbDesc* abb, ShifuCtx** out) {
+  REQUIRE_PTR(out);
+  *out = nullptr;
+  if ((a1 == nullptr) == (abb == nullptr)) return fail(SHIFU_E_NULL, "exactly one of a1 / abb must be given");
+  // validate the descriptor before touching the device so argument errors surface without a GPU
+  A1K a1k; AbbK abbk;
+  if (a1 != nullptr) { int rc = fill_a1k(*a1, a1k); if (rc) return rc; }
+  else { int rc = fill_abbk(*abb, abbk); if (rc) return rc; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(SHIFU_E_NODEVICE, "no CUDA device: libshifu_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(SHIFU_E_RANGE, "device %d out of range (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SHIFU_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  ShifuCtx* c = new (std::nothrow) ShifuCtx();
+  if (c == nullptr) return fail(SHIFU_E_STATE, "out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  int n = 0;
+  if (a1 != nullptr) { c->is_a1 = true; c->a1 = *a1; c->a1k = a1k; n = a1->num_envs; }
+  else { c->is_abb = true; c->abb = *abb; c->abbk = abbk; n = abb->num_envs; }
+  cudaError_t e = cudaMalloc(&c->d_stats, sizeof(double) * (SHIFU_NUM_STATS + 1));
+  if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, sizeof(double) * (SHIFU_NUM_STATS + 1));
+  c->chain_len = (n + COMPACT_CHUNK - 1) / COMPACT_CHUNK + 1;
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_chain, sizeof(unsigned long long) * c->chain_len);
+  if (e == cudaSuccess) e = cudaMemset(c->d_chain, 0, sizeof(unsigned long long) * c->chain_len);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_ticket, sizeof(unsigned) * 2);
+  if (e == cudaSuccess) e = cudaMemset(c->d_ticket, 0, sizeof(unsigned) * 2);
+  if (e == cudaSuccess && c->is_a1) {
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, a1_post_physics_kernel, A1_THREADS, sizeof(A1Smem));
+    const int tiles = (n + A1_TILE - 1) / A1_TILE;
+    const int cap = c->sm_count * (occ > 0 ? occ : 1);
+    c->a1_grid = tiles < cap ? tiles : cap;
+  }
+  if (e != cudaSuccess) {
+    int rc = fail((int)e, "shifu_ctx_create: %s", cudaGetErrorString(e));
+    shifu_ctx_destroy(c);
+    return rc;
+  }
+  c->a1k.stats = c->d_stats;
+  c->abbk.stats = c->d_stats;
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = c;
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_ctx_destroy(ShifuCtx* c) {
+  if (c == nullptr) return SHIFU_OK;
+  cudaFree(c->d_table);
+  cudaFree(c->d_stats);
+  cudaFree(c->d_chain);
+  cudaFree(c->d_ticket);
+  delete c;
+  return SHIFU_OK;
+}
+
+static inline int grid_for(long long work_items, int threads, int sm_count, int per_sm) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sm_count * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int shifu_set_height_map(ShifuCtx* c, const int16_t* hs, int32_t rows, int32_t cols, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(hs);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "height map only applies to an A1 ctx");
+  if (rows < 2 || cols < 2 || (long long)rows * cols > (1LL << 30)) return fail(SHIFU_E_RANGE, "map %dx%d out of range", rows, cols);
+  const char* layout = getenv("SHIFU_TABLE_LAYOUT");
+  const int tiled = (layout != nullptr && strcmp(layout, "rowmajor") == 0) ? 0 : 1;
+  const int trows = rows - 1, tcols = cols - 1;
+  const int tiles_x = (trows + 7) / 8, tiles_y = (tcols + 7) / 8;
+  const size_t elems = tiled ? (size_t)tiles_x * tiles_y * 64 : (size_t)trows * tcols;
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  if (c->d_table != nullptr) { cudaFree(c->d_table); c->d_table = nullptr; }
+  CUDA_TRY(cudaMalloc(&c->d_table, elems * sizeof(short)));
+  CUDA_TRY(cudaMemsetAsync(c->d_table, 0, elems * sizeof(short), S(stream)));
+  build_scan_table_kernel<<<grid_for((long long)trows * tcols, 256, c->sm_count, 8), 256, 0, S(stream)>>>(
+      hs, rows, cols, c->d_table, tiles_y, tiled);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  c->a1k.table = c->d_table;
+  c->a1k.trows = trows; c->a1k.tcols = tcols; c->a1k.tiles_y = tiles_y; c->a1k.tiled = tiled;
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_set_level_sum(ShifuCtx* c, const int64_t* levels, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(levels);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "terrain levels only apply to an A1 ctx");
+  level_sum_kernel<<<1, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(levels), c->a1.num_envs,
+                                             c->d_stats + SHIFU_NUM_STATS);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_pd_torque(ShifuCtx* c, const float* a_in, float* a_out, const float* dof, float* tau, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(a_in); REQUIRE_PTR(dof); REQUIRE_PTR(tau);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_pd_torque needs an A1 ctx");
+  REQUIRE_ALIGNED(dof, 8);
+  const long long total = (long long)c->a1.num_envs * A1_DOF;
+  pd_torque_kernel<<<grid_for(total, 256, c->sm_count, 8), 256, 0, S(stream)>>>(
+      c->a1k, a_in, a_out, reinterpret_cast<const float2*>(dof), tau);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_body_frame(ShifuCtx* c, const float* root, float* lin, float* ang, float* pg, float* gvec, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(root); REQUIRE_PTR(lin); REQUIRE_PTR(ang); REQUIRE_PTR(pg);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_body_frame needs an A1 ctx");
+  body_frame_kernel<<<grid_for(c->a1.num_envs, 256, c->sm_count, 8), 256, 0, S(stream)>>>(c->a1k, root, lin, ang, pg, gvec);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_get_heights(ShifuCtx* c, const float* root, float* mh, int32_t* cell_idx, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(root); REQUIRE_PTR(mh);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_get_heights needs an A1 ctx");
+  if (c->d_table == nullptr) return fail(SHIFU_E_STATE, "call shifu_set_height_map first");
+  const int tiles = (c->a1.num_envs + A1_TILE - 1) / A1_TILE;
+  const int cap = c->sm_count * 8;
+  get_heights_kernel<<<tiles < cap ? tiles : cap, A1_THREADS, 0, S(stream)>>>(c->a1k, root, mh, cell_idx);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_a1_post_physics needs an A1 ctx");
+  if (c->d_table == nullptr) return fail(SHIFU_E_STATE, "call shifu_set_height_map first");
+  REQUIRE_PTR(io->root_state); REQUIRE_PTR(io->dof_state); REQUIRE_PTR(io->contact_state);
+  REQUIRE_PTR(io->actions); REQUIRE_PTR(io->torques); REQUIRE_PTR(io->history); REQUIRE_PTR(io->command);
+  REQUIRE_PTR(io->ep_len); REQUIRE_PTR(io->base_lin_vel); REQUIRE_PTR(io->base_ang_vel);
+  REQUIRE_PTR(io->projected_gravity); REQUIRE_PTR(io->env_origins); REQUIRE_PTR(io->terrain_levels);
+  REQUIRE_PTR(io->terrain_types); REQUIRE_PTR(io->terrain_origins); REQUIRE_PTR(io->dof_targets);
+  REQUIRE_PTR(io->rand_force); REQUIRE_PTR(io->obs_buf); REQUIRE_PTR(io->rew_buf); REQUIRE_PTR(io->reset_buf);
+  REQUIRE_PTR(io->time_out_buf); REQUIRE_PTR(io->contact_term_buf);
+  for (int j = 0; j < c->a1.num_reward_terms; ++j)
+    if (io->ep_sums[j] == nullptr) return fail(SHIFU_E_NULL, "ep_sums[%d] is NULL", j);
+  REQUIRE_ALIGNED(io->dof_state, 16);
+  a1_post_physics_kernel<<<c->a1_grid, A1_THREADS, sizeof(A1Smem), S(stream)>>>(c->a1k, *io);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_abb_post_physics(ShifuCtx* c, const ShifuAbbStepIO* io, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io);
+  if (!c->is_abb) return fail(SHIFU_E_STATE, "shifu_abb_post_physics needs an ABB ctx");
+  REQUIRE_PTR(io->root_state); REQUIRE_PTR(io->body_state); REQUIRE_PTR(io->dof_state); REQUIRE_PTR(io->dof_targets);
+  REQUIRE_PTR(io->ep_len); REQUIRE_PTR(io->obs_buf); REQUIRE_PTR(io->rew_buf); REQUIRE_PTR(io->reset_buf);
+  REQUIRE_PTR(io->time_out_buf); REQUIRE_PTR(io->success_buf);
+  for (int j = 0; j < c->abb.num_reward_terms; ++j)
+    if (io->ep_sums[j] == nullptr) return fail(SHIFU_E_NULL, "ep_sums[%d] is NULL", j);
+  abb_post_physics_kernel<<<grid_for(c->abb.num_envs, 128, c->sm_count, 16), 128, 0, S(stream)>>>(c->abbk, *io);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_compact_reset_ids(ShifuCtx* c, const uint8_t* flags, int32_t n, int64_t* ids, int32_t* n_out, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(flags); REQUIRE_PTR(ids); REQUIRE_PTR(n_out);
+  if (n <= 0) return fail(SHIFU_E_RANGE, "n must be > 0 (got %d)", n);
+  const int chunks = (n + COMPACT_CHUNK - 1) / COMPACT_CHUNK;
+  if (chunks > c->chain_len) return fail(SHIFU_E_RANGE, "n=%d exceeds the ctx's num_envs", n);
+  c->epoch += 1;
+  compact_ids_kernel<<<chunks, COMPACT_THREADS, 0, S(stream)>>>(flags, n, reinterpret_cast<long long*>(ids), n_out,
+                                                               c->d_chain, c->d_ticket, c->epoch);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_history_add(ShifuCtx* c, float* hist, const float* x, int32_t n, int32_t a, int32_t h, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(hist); REQUIRE_PTR(x);
+  if (n <= 0 || a <= 0 || h <= 0) return fail(SHIFU_E_RANGE, "history shape (%d,%d,%d) invalid", n, a, h);
+  const long long rows = (long long)n * a;
+  history_add_kernel<<<grid_for(rows, 256, c->sm_count, 8), 256, 0, S(stream)>>>(hist, x, rows, h);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_clip(ShifuCtx* c, const float* in, float* out, int64_t count, float lim, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(in); REQUIRE_PTR(out);
+  if (count <= 0) return fail(SHIFU_E_RANGE, "count must be > 0");
+  clip_kernel<<<grid_for((count + 3) / 4, 256, c->sm_count, 8), 256, 0, S(stream)>>>(in, out, count, lim);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_a1_reset_idx(ShifuCtx* c, const ShifuA1StepIO* io, const int64_t* ids, int32_t n_ids, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_a1_reset_idx needs an A1 ctx");
+  if (n_ids < 0 || n_ids > c->a1.num_envs) return fail(SHIFU_E_RANGE, "n_ids=%d out of range", n_ids);
+  if (n_ids == 0) return SHIFU_OK;                    // shifu/gym/env.py:115-116
+  REQUIRE_PTR(io->root_state); REQUIRE_PTR(io->dof_state); REQUIRE_PTR(io->history); REQUIRE_PTR(io->command);
+  REQUIRE_PTR(io->ep_len); REQUIRE_PTR(io->env_origins); REQUIRE_PTR(io->terrain_levels);
+  REQUIRE_PTR(io->terrain_types); REQUIRE_PTR(io->terrain_origins); REQUIRE_PTR(io->dof_targets);
+  REQUIRE_PTR(io->rand_force); REQUIRE_PTR(io->reset_buf);
+  for (int j = 0; j < c->a1.num_reward_terms; ++j)
+    if (io->ep_sums[j] == nullptr) return fail(SHIFU_E_NULL, "ep_sums[%d] is NULL", j);
+  a1_reset_idx_kernel<<<grid_for(n_ids, 128, c->sm_count, 16), 128, 0, S(stream)>>>(
+      c->a1k, *io, reinterpret_cast<const long long*>(ids), n_ids);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_collect_stats(ShifuCtx* c, double* out, int64_t* step_dev, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(out);
+  const double n = c->is_a1 ? c->a1.num_envs : c->abb.num_envs;
+  collect_stats_kernel<<<1, 32, 0, S(stream)>>>(c->d_stats, c->d_stats + SHIFU_NUM_STATS, out, n,
+                                                reinterpret_cast<long long*>(step_dev));
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_publish_extras(ShifuCtx* c, const double* stats, float* extras, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(stats); REQUIRE_PTR(extras);
+  const float ls = c->is_a1 ? c->a1.max_episode_length_s : c->abb.max_episode_length_s;
+  const int nt = c->is_a1 ? c->a1.num_reward_terms : c->abb.num_reward_terms;
+  publish_extras_kernel<<<1, 32, 0, S(stream)>>>(stats, extras, ls, nt);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_read_stats_host(ShifuCtx* c, double* host, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(host);
+  CUDA_TRY(cudaMemcpyAsync(host, c->d_stats, sizeof(double) * SHIFU_NUM_STATS, cudaMemcpyDeviceToHost, S(stream)));
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  return SHIFU_OK;
+}

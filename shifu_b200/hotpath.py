@@ -1,0 +1,403 @@
+"""Host-side drivers of the fused CUDA hot path (thin; all arithmetic lives in ``csrc/``).
+
+``A1HotPath`` / ``AbbHotPath`` own a native context, hold the env-side tensors the reference
+keeps on ``ShifuVecEnv`` / ``Robot`` objects (``shifu/gym/env.py:44-63``,
+``examples/a1_conditional/a1_conditional.py:52-62,100-114``) and enqueue the C-ABI calls in the
+reference's order.  The flat simulator tensors (root / dof / contact / body
+state) are *borrowed* from the gym, exactly like the reference borrows them from PhysX.
+
+The ``shifu_b200.gym`` / ``shifu_b200.tasks`` classes wrap these objects behind the reference's
+class API; tests and ``bench.py`` may also drive them directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _native as nv
+
+A1_TERM_CODES = {
+    "tracking_lin_vel": nv.REW_TRACKING_LIN_VEL, "tracking_ang_vel": nv.REW_TRACKING_ANG_VEL,
+    "stabilizing_base": nv.REW_STABILIZING_BASE, "smoothing_action": nv.REW_SMOOTHING_ACTION,
+    "leg_collision": nv.REW_LEG_COLLISION, "torques_penalize": nv.REW_TORQUES,
+}
+# literal constants of the reward methods, examples/a1_conditional/a1_conditional.py:162-192
+A1_TERM_PARAMS = {
+    "tracking_lin_vel": (1.0, 0.25), "tracking_ang_vel": (0.5, 0.25), "stabilizing_base": (-2.0, -0.005),
+    "smoothing_action": (-0.005, 0.0), "leg_collision": (-1.0, 0.1), "torques_penalize": (-2e-5, 0.0),
+}
+ABB_TERM_CODES = {"reward_reaching": nv.REW_ABB_REACHING, "reward_success": nv.REW_ABB_SUCCESS}
+# examples/abb_pushbox_vision/a_prior_stage.py:118-131
+ABB_TERM_PARAMS = {"reward_reaching": (0.1, 0.05), "reward_success": (200.0, 0.02)}
+
+
+def compile_reward_terms(names: Sequence[str], codes: Dict[str, int], params: Dict[str, tuple]):
+    """The reward-term registry: ``build_reward_functions()`` names -> (enum, p0, p1) in list order
+    (``shifu/gym/env.py:160-166`` keys ``episode_rewards`` by ``fn.__name__``)."""
+    if len(names) == 0:
+        raise ValueError("at least one reward term is required (env.py:161)")
+    if len(names) > nv.MAX_TERMS:
+        raise ValueError(f"at most {nv.MAX_TERMS} fused reward terms are supported")
+    out = []
+    for n in names:
+        if n not in codes:
+            raise KeyError(f"reward term {n!r} has no fused implementation; known: {sorted(codes)}")
+        out.append((codes[n], float(params[n][0]), float(params[n][1])))
+    return out
+
+
+def a1_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
+            terms: Sequence[str] = tuple(A1_TERM_CODES), term_params: Optional[Dict[str, tuple]] = None,
+            q0=(0.1, 0.8, -1.5, 0.1, 0.8, -1.5, -0.1, 0.8, -1.5, -0.1, 0.8, -1.5),
+            kp=(20.,) * 12, kd=(.5,) * 12, torque_limit=(20., 55., 55.) * 4,
+            points_x=(-0.8, -0.7, -0.6, -0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8),
+            points_y=(-0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5),
+            border_size=25., horizontal_scale=0.1, vertical_scale=0.005, max_episode_length=500,
+            max_episode_length_s=10., default_root=(0, 0, 0.42, 0, 0, 0, 1.), curriculum=True,
+            max_terrain_level=10, num_terrain_types=20, env_length=8., base_body=0,
+            leg_bodies=(2, 3, 6, 7, 10, 11, 14, 15), force_body=0, root_stride=1, root_offset=0,
+            action_scale=0.5, clip_actions=1., clip_obs=100.) -> nv.A1Desc:
+    """Defaults = the constants of ``examples/a1_conditional``."""
+    d = nv.A1Desc()
+    d.abi_version = nv.ABI_VERSION
+    d.num_envs, d.env_offset, d.rng_seed = num_envs, env_offset, rng_seed
+    d.num_dof, d.num_bodies, d.num_hist, d.num_obs = 12, 17, 3, 259
+    d.base_body, d.force_body = base_body, force_body
+    d.num_leg_bodies = len(leg_bodies)
+    for i, b in enumerate(leg_bodies):
+        d.leg_bodies[i] = b
+    d.root_stride, d.root_offset = root_stride, root_offset
+    for i in range(12):
+        d.q0[i], d.kp[i], d.kd[i], d.torque_limit[i] = q0[i], kp[i], kd[i], torque_limit[i]
+    d.action_scale, d.clip_actions, d.clip_obs = action_scale, clip_actions, clip_obs
+    d.num_points_x, d.num_points_y = len(points_x), len(points_y)
+    if len(points_x) > nv.MAX_PX or len(points_y) > nv.MAX_PY:
+        raise ValueError("measured-point grid larger than the compiled 17x11")
+    for i, v in enumerate(points_x):
+        d.points_x[i] = v
+    for i, v in enumerate(points_y):
+        d.points_y[i] = v
+    d.border_size, d.horizontal_scale, d.vertical_scale = border_size, horizontal_scale, vertical_scale
+    d.height_offset, d.height_clip = 0.5, 1.0
+    d.max_episode_length, d.max_episode_length_s = int(max_episode_length), max_episode_length_s
+    d.contact_term_force = 1.0
+    for i in range(7):
+        d.default_root[i] = default_root[i]
+    d.reset_xy_range, d.push_force_max = 1.0, 5.0
+    for i in range(3):
+        d.cmd_low[i], d.cmd_high[i] = -1.0, 1.0
+    d.curriculum = int(bool(curriculum))
+    d.max_terrain_level, d.num_terrain_types = max_terrain_level, num_terrain_types
+    d.level_up_distance, d.level_down_factor = env_length / 2, 0.5
+    comp = compile_reward_terms(list(terms), A1_TERM_CODES, {**A1_TERM_PARAMS, **(term_params or {})})
+    d.num_reward_terms = len(comp)
+    for i, (code, p0, p1) in enumerate(comp):
+        d.reward_terms[i] = code
+        d.reward_params[i][0], d.reward_params[i][1] = p0, p1
+    return d
+
+
+class _Ctx:
+    """RAII holder of a native ShifuCtx."""
+
+    def __init__(self, device: torch.device, a1: Optional[nv.A1Desc] = None, abb: Optional[nv.AbbDesc] = None):
+        self.lib = nv.load()
+        if device.type != "cuda":
+            raise nv.ShifuNativeError(nv.E_NODEVICE, f"device {device} is not CUDA: the shifu_b200 hot "
+                                                     "path has no CPU fallback")
+        self.handle = C.c_void_p()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        nv.check(self.lib.shifu_ctx_create(idx, C.byref(a1) if a1 is not None else None,
+                                           C.byref(abb) if abb is not None else None, C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.shifu_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class A1HotPath:
+    """Fused A1 step.  ``root_state`` / ``dof_state`` / ``contact_state`` are the gym's flat tensors."""
+
+    def __init__(self, desc: nv.A1Desc, *, root_state, dof_state, contact_state, height_samples,
+                 terrain_origins, terrain_types, env_origins, terms: Sequence[str] = tuple(A1_TERM_CODES),
+                 carry_body_frame: bool = False, want_measured_heights: bool = True):
+        dev = root_state.device
+        self.device = dev
+        self.desc = desc
+        self.n = n = desc.num_envs
+        self.terms = list(terms)
+        self.ctx = _Ctx(dev, a1=desc)
+        self.lib = self.ctx.lib
+        f = dict(device=dev, dtype=torch.float)
+        # borrowed simulator tensors
+        self.root_state, self.dof_state, self.contact_state = root_state, dof_state, contact_state
+        # terrain (isaac_gym.py:336-347)
+        self.height_samples = height_samples.to(dev).contiguous()
+        assert self.height_samples.dtype == torch.int16
+        self.terrain_origins = terrain_origins.to(**f).contiguous()
+        self.terrain_types = terrain_types.to(dev, torch.long).contiguous()
+        self.env_origins = env_origins            # (N,3) fp32, shared with the gym façade
+        # env-side buffers (env.py:44-63, a1_conditional.py:52-62,100-114)
+        self.actions = torch.zeros(n, 12, **f)
+        self.torques = torch.zeros(n, 12, **f)
+        self.history = torch.zeros(n, 12, 3, **f)
+        self.command = torch.zeros(n, 3, **f)
+        self.ep_len = torch.zeros(n, device=dev, dtype=torch.long)
+        self.ep_sums = {k: torch.zeros(n, **f) for k in self.terms}
+        self.base_lin_vel = torch.zeros(n, 3, **f)
+        self.base_ang_vel = torch.zeros(n, 3, **f)
+        self.projected_gravity = torch.zeros(n, 3, **f)
+        self.gravity_vec = torch.tensor([0., 0., -1.], **f).repeat(n, 1)
+        self.terrain_levels = torch.zeros(n, device=dev, dtype=torch.long)
+        self.dof_targets = torch.zeros(n, 12, **f)
+        self.rand_force = torch.zeros(n, 17, 3, **f)
+        self.obs_buf = torch.zeros(n, 259, **f)
+        self.rew_buf = torch.zeros(n, **f)
+        self.reset_buf = torch.ones(n, device=dev, dtype=torch.bool)
+        self.time_out_buf = torch.zeros(n, device=dev, dtype=torch.bool)
+        self.contact_terminate_buf = torch.zeros(n, device=dev, dtype=torch.bool)
+        self.measured_heights = torch.zeros(n, 187, **f) if want_measured_heights else None
+        self.reset_ids = torch.zeros(n, device=dev, dtype=torch.long)
+        self.n_reset = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.stats = torch.zeros(nv.NUM_STATS, device=dev, dtype=torch.double)
+        self.extras_arr = torch.zeros(nv.NUM_STATS, **f)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.long)
+        self.step_counter = 0
+        self.carry_body_frame = carry_body_frame
+        self._io = None
+        nv.check(self.lib.shifu_set_height_map(self.ctx.handle, nv.ptr(self.height_samples),
+                                               self.height_samples.shape[0], self.height_samples.shape[1],
+                                               nv.current_stream()))
+        self.sync_level_sum()
+
+    # ------------------------------------------------------------------
+    def _build_io(self, use_step_dev: bool) -> nv.A1StepIO:
+        io = nv.A1StepIO()
+        p = nv.ptr
+        io.root_state, io.dof_state, io.contact_state = p(self.root_state), p(self.dof_state), p(self.contact_state)
+        io.actions, io.torques, io.history, io.command = p(self.actions), p(self.torques), p(self.history), p(self.command)
+        io.ep_len = p(self.ep_len)
+        for i, k in enumerate(self.terms):
+            io.ep_sums[i] = p(self.ep_sums[k])
+        io.base_lin_vel, io.base_ang_vel = p(self.base_lin_vel), p(self.base_ang_vel)
+        io.projected_gravity = p(self.projected_gravity)
+        io.env_origins, io.terrain_levels = p(self.env_origins), p(self.terrain_levels)
+        io.terrain_types, io.terrain_origins = p(self.terrain_types), p(self.terrain_origins)
+        io.dof_targets, io.rand_force = p(self.dof_targets), p(self.rand_force)
+        io.obs_buf, io.rew_buf, io.reset_buf = p(self.obs_buf), p(self.rew_buf), p(self.reset_buf)
+        io.time_out_buf, io.contact_term_buf = p(self.time_out_buf), p(self.contact_terminate_buf)
+        io.measured_heights = p(self.measured_heights)
+        io.step = self.step_counter
+        io.step_dev = p(self.step_dev) if use_step_dev else None
+        io.carry_body_frame = int(self.carry_body_frame)
+        return io
+
+    def io(self, use_step_dev: bool = False) -> nv.A1StepIO:
+        if self._io is None or bool(self._io.step_dev) != use_step_dev:
+            self._io = self._build_io(use_step_dev)
+        self._io.step = self.step_counter
+        self._io.carry_body_frame = int(self.carry_body_frame)
+        return self._io
+
+    def invalidate_io(self):
+        """Call after re-binding any tensor attribute (pointers are cached)."""
+        self._io = None
+
+    def sync_level_sum(self):
+        nv.check(self.lib.shifu_set_level_sum(self.ctx.handle, nv.ptr(self.terrain_levels), nv.current_stream()))
+
+    # -- individual rows -------------------------------------------------
+    def pd_torque(self, raw_actions: Optional[torch.Tensor] = None):
+        """Row a2 (+a1 when ``raw_actions`` is given: env.actions = clip(0.5*a, +-1) is produced too)."""
+        s = nv.current_stream()
+        if raw_actions is not None:
+            nv.check(self.lib.shifu_pd_torque(self.ctx.handle, nv.ptr(raw_actions), nv.ptr(self.actions),
+                                              nv.ptr(self.dof_state), nv.ptr(self.torques), s))
+        else:
+            nv.check(self.lib.shifu_pd_torque(self.ctx.handle, nv.ptr(self.actions), None,
+                                              nv.ptr(self.dof_state), nv.ptr(self.torques), s))
+
+    def body_frame(self):
+        """Row a3: LeggedRobot.post_step on the CURRENT content of root_state (S_prev, D7)."""
+        nv.check(self.lib.shifu_body_frame(self.ctx.handle, nv.ptr(self.root_state), nv.ptr(self.base_lin_vel),
+                                           nv.ptr(self.base_ang_vel), nv.ptr(self.projected_gravity),
+                                           nv.ptr(self.gravity_vec), nv.current_stream()))
+
+    def get_heights(self, out: Optional[torch.Tensor] = None, cell_idx: Optional[torch.Tensor] = None):
+        """Row a5 stand-alone."""
+        out = self.measured_heights if out is None else out
+        nv.check(self.lib.shifu_get_heights(self.ctx.handle, nv.ptr(self.root_state), nv.ptr(out),
+                                            nv.ptr(cell_idx), nv.current_stream()))
+        return out
+
+    def post_physics(self, use_step_dev: bool = False):
+        """Rows a5-a7, a9-a14 in one kernel.  Advances the host step counter (env.py:96)."""
+        self.step_counter += 1
+        nv.check(self.lib.shifu_a1_post_physics(self.ctx.handle, C.byref(self.io(use_step_dev)), nv.current_stream()))
+
+    def compact(self):
+        """Row a8: ascending reset ids + count (device)."""
+        nv.check(self.lib.shifu_compact_reset_ids(self.ctx.handle, nv.ptr(self.reset_buf), self.n,
+                                                  nv.ptr(self.reset_ids), nv.ptr(self.n_reset), nv.current_stream()))
+
+    def collect_stats(self, advance_step_dev: bool = False):
+        nv.check(self.lib.shifu_collect_stats(self.ctx.handle, nv.ptr(self.stats),
+                                              nv.ptr(self.step_dev) if advance_step_dev else None,
+                                              nv.current_stream()))
+
+    def publish_extras(self):
+        nv.check(self.lib.shifu_publish_extras(self.ctx.handle, nv.ptr(self.stats), nv.ptr(self.extras_arr),
+                                               nv.current_stream()))
+
+    def reset_idx(self, env_ids: Optional[torch.Tensor], allreduce=None):
+        """Rows a9-a11 stand-alone (``A1Conditional.reset_idx``); ``None`` = all envs."""
+        n_ids = self.n if env_ids is None else int(env_ids.numel())
+        if env_ids is not None:
+            env_ids = env_ids.to(self.device, torch.long).contiguous()
+        nv.check(self.lib.shifu_a1_reset_idx(self.ctx.handle, C.byref(self.io(False)), nv.ptr(env_ids), n_ids,
+                                             nv.current_stream()))
+        if n_ids > 0:                       # log_info runs inside reset_idx (env.py:124-130)
+            self.collect_stats()
+            if allreduce is not None:
+                allreduce(self.stats)
+            self.publish_extras()
+
+    def finalize(self, allreduce=None, advance_step_dev: bool = False):
+        """compaction + stats -> (optional all-reduce over ranks) -> extras."""
+        self.compact()
+        self.collect_stats(advance_step_dev)
+        if allreduce is not None:
+            allreduce(self.stats)
+        self.publish_extras()
+
+    # -- the whole control step without a simulator in between (bench / graph capture) ------
+    def step_resident(self, raw_actions: torch.Tensor, decimation: int = 4, use_step_dev: bool = False,
+                      allreduce=None):
+        """PD x decimation, (body-frame unless carried), fused post-physics, compaction, stats —
+        on whatever the flat state tensors currently hold."""
+        self.pd_torque(raw_actions)
+        for _ in range(decimation - 1):
+            self.pd_torque()
+        if not self.carry_body_frame:
+            self.body_frame()
+        self.post_physics(use_step_dev)
+        self.finalize(allreduce, advance_step_dev=use_step_dev)
+
+    def extras(self) -> Dict:
+        """``extras`` dict of 0-dim views (env.py:124-130, a1_conditional.py:126-129)."""
+        ep = {k: self.extras_arr[i] for i, k in enumerate(self.terms)}
+        ep["terrain_levels"] = self.extras_arr[nv.STAT_LEVEL_SUM]
+        return {"episode": ep, "time_outs": self.time_out_buf}
+
+    def reset_id_list(self) -> torch.Tensor:
+        """Host-synchronising view of the compacted ids (like ``nonzero`` in the reference)."""
+        return self.reset_ids[: int(self.n_reset.item())]
+
+
+def abb_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
+             terms: Sequence[str] = tuple(ABB_TERM_CODES)) -> nv.AbbDesc:
+    """Constants of ``examples/abb_pushbox_vision`` prior stage (task_config.py:49-91)."""
+    d = nv.AbbDesc()
+    d.abi_version = nv.ABI_VERSION
+    d.num_envs, d.env_offset, d.rng_seed = num_envs, env_offset, rng_seed
+    d.num_actors, d.num_bodies, d.num_dof, d.ee_body = 4, 10, 6, 6
+    d.robot_actor, d.table_actor, d.cube_actor, d.goal_actor = 0, 1, 2, 3
+    for i, v in enumerate((-0.2, -0.2, 0.11)):
+        d.min_ee_pos[i] = v
+    for i, v in enumerate((0.2, 0.2, 0.14)):
+        d.max_ee_pos[i] = v
+    for i, v in enumerate((0., 0.6437, 0.1748, 0., 0.7541, 0.)):
+        d.q0[i] = v
+    for i, v in enumerate((-0.48, 0, 0, 0, 0, 0, 1)):
+        d.robot_root[i] = v
+    for i, v in enumerate((0, 0, 0.05, 0, 0, 0, 1)):
+        d.table_root[i] = v
+    for i, (lo, hi) in enumerate(((-0.1, 0.1), (-0.1, 0.1), (0.125, 0.125))):
+        d.box_pos_low[i], d.box_pos_high[i] = lo, hi
+    d.goal_z = 0.1
+    d.success_distance = 0.02
+    d.max_episode_length, d.max_episode_length_s, d.clip_obs = 200, 20., 10.
+    comp = compile_reward_terms(list(terms), ABB_TERM_CODES, ABB_TERM_PARAMS)
+    d.num_reward_terms = len(comp)
+    for i, (code, p0, p1) in enumerate(comp):
+        d.reward_terms[i] = code
+        d.reward_params[i][0], d.reward_params[i][1] = p0, p1
+    return d
+
+
+class AbbHotPath:
+    def __init__(self, desc: nv.AbbDesc, *, root_state, body_state, dof_state,
+                 terms: Sequence[str] = tuple(ABB_TERM_CODES)):
+        dev = root_state.device
+        self.device, self.desc, self.n = dev, desc, desc.num_envs
+        n = self.n
+        self.terms = list(terms)
+        self.ctx = _Ctx(dev, abb=desc)
+        self.lib = self.ctx.lib
+        f = dict(device=dev, dtype=torch.float)
+        self.root_state, self.body_state, self.dof_state = root_state, body_state, dof_state
+        self.dof_targets = torch.zeros(n, 6, **f)
+        self.ep_len = torch.zeros(n, device=dev, dtype=torch.long)
+        self.ep_sums = {k: torch.zeros(n, **f) for k in self.terms}
+        self.obs_buf = torch.zeros(n, 6, **f)
+        self.rew_buf = torch.zeros(n, **f)
+        self.reset_buf = torch.ones(n, device=dev, dtype=torch.bool)
+        self.time_out_buf = torch.zeros(n, device=dev, dtype=torch.bool)
+        self.success_buf = torch.zeros(n, device=dev, dtype=torch.bool)
+        self.reset_ids = torch.zeros(n, device=dev, dtype=torch.long)
+        self.n_reset = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.stats = torch.zeros(nv.NUM_STATS, device=dev, dtype=torch.double)
+        self.extras_arr = torch.zeros(nv.NUM_STATS, **f)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.long)
+        self.step_counter = 0
+        self._io = None
+
+    def io(self, use_step_dev: bool = False) -> nv.AbbStepIO:
+        if self._io is None or bool(self._io.step_dev) != use_step_dev:
+            io = nv.AbbStepIO()
+            p = nv.ptr
+            io.root_state, io.body_state, io.dof_state = p(self.root_state), p(self.body_state), p(self.dof_state)
+            io.dof_targets, io.ep_len = p(self.dof_targets), p(self.ep_len)
+            for i, k in enumerate(self.terms):
+                io.ep_sums[i] = p(self.ep_sums[k])
+            io.obs_buf, io.rew_buf, io.reset_buf = p(self.obs_buf), p(self.rew_buf), p(self.reset_buf)
+            io.time_out_buf, io.success_buf = p(self.time_out_buf), p(self.success_buf)
+            io.step_dev = p(self.step_dev) if use_step_dev else None
+            self._io = io
+        self._io.step = self.step_counter
+        return self._io
+
+    def post_physics(self, use_step_dev: bool = False):
+        self.step_counter += 1
+        nv.check(self.lib.shifu_abb_post_physics(self.ctx.handle, C.byref(self.io(use_step_dev)), nv.current_stream()))
+
+    def finalize(self, allreduce=None, advance_step_dev: bool = False):
+        s = nv.current_stream()
+        nv.check(self.lib.shifu_compact_reset_ids(self.ctx.handle, nv.ptr(self.reset_buf), self.n,
+                                                  nv.ptr(self.reset_ids), nv.ptr(self.n_reset), s))
+        nv.check(self.lib.shifu_collect_stats(self.ctx.handle, nv.ptr(self.stats),
+                                              nv.ptr(self.step_dev) if advance_step_dev else None, s))
+        if allreduce is not None:
+            allreduce(self.stats)
+        nv.check(self.lib.shifu_publish_extras(self.ctx.handle, nv.ptr(self.stats), nv.ptr(self.extras_arr), s))
+
+    def step_resident(self, use_step_dev: bool = False, allreduce=None):
+        self.post_physics(use_step_dev)
+        self.finalize(allreduce, advance_step_dev=use_step_dev)
+
+    def extras(self) -> Dict:
+        ep = {k: self.extras_arr[i] for i, k in enumerate(self.terms)}
+        ep["success_rate"] = self.extras_arr[nv.STAT_SUCCESS]
+        return {"episode": ep, "time_outs": self.time_out_buf}
+
+    def reset_id_list(self) -> torch.Tensor:
+        return self.reset_ids[: int(self.n_reset.item())]
