@@ -216,6 +216,9 @@ typedef struct ShifuAbbStepIO {
 /* Replaces the buffer/constant set-up of ShifuVecEnv.__init__ (shifu/gym/env.py:19-63).
  * Exactly one of a1 / abb may be non-NULL per ctx.  `device` is the CUDA ordinal. */
 int shifu_ctx_create(int device, const ShifuA1Desc* a1, const ShifuAbbDesc* abb, ShifuCtx** out);
+/* Task-less context for envs whose hooks stay user-written torch code: only the generic rows
+ * (shifu_compact_reset_ids, shifu_history_add, shifu_clip) may be called on it. */
+int shifu_ctx_create_util(int device, int32_t num_envs, ShifuCtx** out);
 int shifu_ctx_destroy(ShifuCtx* ctx);
 const char* shifu_last_error(void);
 int shifu_abi_version(void);

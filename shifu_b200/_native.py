@@ -99,6 +99,7 @@ _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
     "shifu_ctx_create": [C.c_int, C.POINTER(A1Desc), C.POINTER(AbbDesc), C.POINTER(_VP)],
+    "shifu_ctx_create_util": [C.c_int, _I32, C.POINTER(_VP)],
     "shifu_ctx_destroy": [_VP],
     "shifu_last_error": [],
     "shifu_abi_version": [],

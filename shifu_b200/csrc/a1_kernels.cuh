@@ -90,24 +90,45 @@ __global__ void build_scan_table_kernel(const short* __restrict__ H, int rows, i
 // ------------------------------------------------------------------------------------------
 // Row a1/a2: (optional) action scale+clip, then one PD substep.
 //   tau = clip(kp*((a + q0) - q) - kd*qd, +-tau_max)       a1_conditional.py:66-67
-// One thread per (env, dof) pair; dof_state is read as float2 (pos, vel) — fully coalesced.
+// One thread per group of 4 consecutive dofs (3 groups per env): one 128-bit action load, two
+// 128-bit dof_state loads (4 x (pos, vel)), one 128-bit torque store — all fully coalesced.
+// Pure streaming: 192 B/env per substep (240 B when the clipped actions are written too).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pd_one(float a, float q0, float kp, float kd, float lim, float q, float qd) {
+  const float e = sub_rn(add_rn(a, q0), q);
+  return clampf(sub_rn(mul_rn(kp, e), mul_rn(kd, qd)), -lim, lim);
+}
+
 __global__ void __launch_bounds__(256)
-pd_torque_kernel(const __grid_constant__ A1K k, const float* __restrict__ a_in, float* __restrict__ a_out,
-                 const float2* __restrict__ dof, float* __restrict__ tau) {
-  const long long total = (long long)k.n * A1_DOF;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int d = (int)(i % A1_DOF);
-    float a = a_in[i];
-    if (a_out != nullptr) {
-      a = clampf(mul_rn(a, k.action_scale), -k.clip_actions, k.clip_actions);
-      a_out[i] = a;
+pd_torque_kernel(const __grid_constant__ A1K k, const float4* __restrict__ a_in, float4* __restrict__ a_out,
+                 const float4* __restrict__ dof, float4* __restrict__ tau) {
+  __shared__ __align__(16) float c_q0[A1_DOF], c_kp[A1_DOF], c_kd[A1_DOF], c_lim[A1_DOF];
+  if (threadIdx.x < A1_DOF) {
+    c_q0[threadIdx.x] = k.q0[threadIdx.x];
+    c_kp[threadIdx.x] = k.kp[threadIdx.x];
+    c_kd[threadIdx.x] = k.kd[threadIdx.x];
+    c_lim[threadIdx.x] = k.tau_max[threadIdx.x];
+  }
+  __syncthreads();
+  const unsigned total = (unsigned)k.n * (A1_DOF / 4);          // <= 3 * 2^31 / 4 quads
+  const float sc = k.action_scale, ca = k.clip_actions;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const unsigned g = q % 3u;                                    // which third of the env's 12 dofs
+    float4 a = __ldg(a_in + q);
+    if (a_out != nullptr) {                                       // a1_conditional.py:123, env.py:87
+      a.x = clampf(mul_rn(a.x, sc), -ca, ca); a.y = clampf(mul_rn(a.y, sc), -ca, ca);
+      a.z = clampf(mul_rn(a.z, sc), -ca, ca); a.w = clampf(mul_rn(a.w, sc), -ca, ca);
+      a_out[q] = a;
     }
-    const float2 s = dof[i];
-    const float e = sub_rn(add_rn(a, k.q0[d]), s.x);
-    const float t = sub_rn(mul_rn(k.kp[d], e), mul_rn(k.kd[d], s.y));
-    tau[i] = clampf(t, -k.tau_max[d], k.tau_max[d]);
+    const float4 s0 = __ldg(dof + 2 * (size_t)q), s1 = __ldg(dof + 2 * (size_t)q + 1);
+    const float4 q0 = reinterpret_cast<const float4*>(c_q0)[g], kp = reinterpret_cast<const float4*>(c_kp)[g];
+    const float4 kd = reinterpret_cast<const float4*>(c_kd)[g], lm = reinterpret_cast<const float4*>(c_lim)[g];
+    float4 t;
+    t.x = pd_one(a.x, q0.x, kp.x, kd.x, lm.x, s0.x, s0.y);
+    t.y = pd_one(a.y, q0.y, kp.y, kd.y, lm.y, s0.z, s0.w);
+    t.z = pd_one(a.z, q0.z, kp.z, kd.z, lm.z, s1.x, s1.y);
+    t.w = pd_one(a.w, q0.w, kp.w, kd.w, lm.w, s1.z, s1.w);
+    tau[q] = t;
   }
 }
 
@@ -365,263 +386,4 @@ a1_reset_idx_kernel(const __grid_constant__ A1K k, const __grid_constant__ Shifu
     a1_log_sums(k, reset, st_sum, level_delta, lane);
   }
 }
-
-// ------------------------------------------------------------------------------------------
-// K-main: the fused post-physics step (ShifuVecEnv.post_step, shifu/gym/env.py:93-106, with the
-// A1 hooks, + obs clip env.py:90).  One CTA = A1_TILE consecutive envs, four phases:
-//   A  coalesced 128-bit loads of the tile's root/dof/contact/history/torque/action rows -> smem
-//   B  warp 0, one lane per env: ep_len, termination, reward terms + episode sums, reset
-//      (curriculum, Philox draws, state rewrite, log sums), obs head (72 cols), history push,
-//      carried body-frame velocities
-//   C  all warps, thread t owns scan point t: 187-point height scan per env, obs cols 72..258
-//      streamed straight to HBM (each warp writes 128 contiguous bytes)
-//   D  coalesced write-back of the obs head and the history tile
-// ------------------------------------------------------------------------------------------
-struct A1Smem {
-  float root[A1_TILE][13];
-  float dof[A1_TILE][A1_DOF * 2];
-  float contact[A1_TILE][A1_BODIES * 3];
-  float hist[A1_TILE][A1_DOF * A1_HIST];
-  float tau[A1_TILE][A1_DOF];
-  float act[A1_TILE][A1_DOF];
-  float head[A1_TILE][A1_HEAD];
-  ScanEnv ev[A1_TILE];
-  float zb[A1_TILE];
-};
-
-// Copy `n` floats global -> shared with float4 when both sides are 16-byte aligned.
-__device__ __forceinline__ void load_span(float* __restrict__ dst, const float* __restrict__ src, int n,
-                                          int tid, int nthreads) {
-  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
-    const int n4 = n >> 2;
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < n4; i += nthreads) d4[i] = __ldg(s4 + i);
-    for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
-  } else {
-    for (int i = tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
-  }
-}
-
-__device__ __forceinline__ void store_span(float* __restrict__ dst, const float* __restrict__ src, int n,
-                                           int tid, int nthreads) {
-  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
-    const int n4 = n >> 2;
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < n4; i += nthreads) d4[i] = s4[i];
-    for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
-  } else {
-    for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
-  }
-}
-
-__global__ void __launch_bounds__(A1_THREADS)
-a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  A1Smem& s = *reinterpret_cast<A1Smem*>(smem_raw);
-  const int t = threadIdx.x;
-  const long long step = (io.step_dev != nullptr) ? *io.step_dev : io.step;
-  // scan point owned by this thread (thread 187..191 idle in phase C)
-  const float bx = k.px[t % A1_NX], by = k.py[(t / A1_NX) % A1_NY];
-
-  for (int e0 = blockIdx.x * A1_TILE; e0 < k.n; e0 += gridDim.x * A1_TILE) {
-    const int ne = min(A1_TILE, k.n - e0);
-    const int ge = e0 + t;                 // env of this lane in phase B
-    const bool lane_env = (t < ne);
-
-    // ---- prefetch the per-env scalars warp 0 needs in phase B (in flight during phase A) ----
-    long long len = 0;
-    float cmd[3] = {0, 0, 0}, lin[3] = {0, 0, 0}, ang[3] = {0, 0, 0};
-    float esum[SHIFU_MAX_REWARD_TERMS];
-    if (lane_env) {
-      len = io.ep_len[ge];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        cmd[j] = io.command[ge * 3LL + j];
-        lin[j] = io.base_lin_vel[ge * 3LL + j];
-        ang[j] = io.base_ang_vel[ge * 3LL + j];
-      }
-#pragma unroll
-      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) esum[j] = (j < k.n_terms) ? io.ep_sums[j][ge] : 0.0f;
-    }
-
-    // ---- phase A ----
-    if (k.root_stride == 1 && k.root_offset == 0) {
-      load_span(&s.root[0][0], io.root_state + (long long)e0 * 13, ne * 13, t, A1_THREADS);
-    } else {
-      for (int i = t; i < ne * 13; i += A1_THREADS) {
-        const int e = i / 13, c = i % 13;
-        s.root[e][c] = io.root_state[((long long)(e0 + e) * k.root_stride + k.root_offset) * 13 + c];
-      }
-    }
-    load_span(&s.dof[0][0], io.dof_state + (long long)e0 * (A1_DOF * 2), ne * A1_DOF * 2, t, A1_THREADS);
-    load_span(&s.contact[0][0], io.contact_state + (long long)e0 * (A1_BODIES * 3), ne * A1_BODIES * 3, t,
-              A1_THREADS);
-    load_span(&s.hist[0][0], io.history + (long long)e0 * (A1_DOF * A1_HIST), ne * A1_DOF * A1_HIST, t,
-              A1_THREADS);
-    load_span(&s.tau[0][0], io.torques + (long long)e0 * A1_DOF, ne * A1_DOF, t, A1_THREADS);
-    load_span(&s.act[0][0], io.actions + (long long)e0 * A1_DOF, ne * A1_DOF, t, A1_THREADS);
-    __syncthreads();
-
-    // ---- phase B ----
-    if (t < 32) {
-      bool reset = false;
-      double st_sum[SHIFU_MAX_REWARD_TERMS];
-#pragma unroll
-      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) st_sum[j] = 0.0;
-      long long level_delta = 0;
-      if (lane_env) {
-        const int e = t;
-        // heights are measured at the PRE-reset pose (isaac_gym.py:320-322 runs before post_step)
-        s.ev[e] = make_scan_env(s.root[e]);
-        len += 1;                                                          // env.py:95
-        // -- termination, a1_conditional.py:146-150
-        const float* fb = &s.contact[e][k.base_body * 3];
-        const bool contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
-        const bool time_out = len > k.max_len;
-        reset = contact_term | time_out;
-        // -- reward terms in list order, env.py:180-185
-        float rew = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
-          if (j < k.n_terms) {
-            const float p0 = k.rp[j][0], p1 = k.rp[j][1];
-            float r = 0.0f;
-            switch (k.terms[j]) {
-              case SHIFU_REW_TRACKING_LIN_VEL: {
-                const float dx = sub_rn(cmd[0], lin[0]), dy = sub_rn(cmd[1], lin[1]);
-                const float err = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-                r = mul_rn(p0, expf(div_rn(-err, p1)));
-              } break;
-              case SHIFU_REW_TRACKING_ANG_VEL: {
-                const float d = sub_rn(cmd[2], ang[2]);
-                r = mul_rn(p0, expf(div_rn(-mul_rn(d, d), p1)));
-              } break;
-              case SHIFU_REW_STABILIZING_BASE: {
-                const float zv = mul_rn(p0, mul_rn(lin[2], lin[2]));
-                const float av = mul_rn(p1, add_rn(mul_rn(ang[0], ang[0]), mul_rn(ang[1], ang[1])));
-                r = add_rn(zv, av);
-              } break;
-              case SHIFU_REW_SMOOTHING_ACTION: {
-                float f1 = 0.0f, f2 = 0.0f;
-#pragma unroll
-                for (int d = 0; d < A1_DOF; ++d) {
-                  const float a0 = s.hist[e][d * A1_HIST + 0], a1 = s.hist[e][d * A1_HIST + 1],
-                              a2 = s.hist[e][d * A1_HIST + 2];
-                  const float d1 = sub_rn(a1, a0);
-                  const float d2 = add_rn(sub_rn(a2, mul_rn(2.0f, a1)), a0);
-                  f1 = add_rn(f1, mul_rn(d1, d1));
-                  f2 = add_rn(f2, mul_rn(d2, d2));
-                }
-                r = mul_rn(p0, add_rn(f1, f2));
-              } break;
-              case SHIFU_REW_LEG_COLLISION: {
-                int cnt = 0;
-                for (int b = 0; b < k.n_leg; ++b) {
-                  const float* f = &s.contact[e][k.leg[b] * 3];
-                  cnt += (norm3_fma(f[0], f[1], f[2]) > p1) ? 1 : 0;
-                }
-                r = mul_rn(p0, (float)cnt);
-              } break;
-              case SHIFU_REW_TORQUES: {
-                float acc = 0.0f;
-#pragma unroll
-                for (int d = 0; d < A1_DOF; ++d) acc = add_rn(acc, mul_rn(s.tau[e][d], s.tau[e][d]));
-                r = mul_rn(p0, acc);
-              } break;
-              default: break;
-            }
-            esum[j] = add_rn(esum[j], r);
-            rew = add_rn(rew, r);
-          }
-        }
-        io.rew_buf[ge] = rew;
-        io.reset_buf[ge] = reset ? 1 : 0;
-        io.time_out_buf[ge] = time_out ? 1 : 0;
-        io.contact_term_buf[ge] = contact_term ? 1 : 0;
-
-        // -- reset (env.py:101-102 -> a1_conditional.py:116-120)
-        if (reset)
-          a1_reset_env<true>(k, io, step, ge, s.root[e], s.dof[e], s.hist[e], cmd, esum, len, st_sum,
-                             level_delta);
-        io.ep_len[ge] = len;
-#pragma unroll
-        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j)
-          if (j < k.n_terms) io.ep_sums[j][ge] = esum[j];
-
-        // -- observation head, a1_conditional.py:131-144 (post-reset command/dof/history, D8)
-        float* h = s.head[e];
-        const float c = k.clip_obs;
-        h[0] = clampf(cmd[0], -c, c); h[1] = clampf(cmd[1], -c, c); h[2] = clampf(cmd[2], -c, c);
-        h[3] = clampf(lin[0], -c, c); h[4] = clampf(lin[1], -c, c); h[5] = clampf(lin[2], -c, c);
-        h[6] = clampf(ang[0], -c, c); h[7] = clampf(ang[1], -c, c); h[8] = clampf(ang[2], -c, c);
-        h[9] = 0.0f; h[10] = 0.0f; h[11] = clampf(-1.0f, -c, c);          // gravity_vec, robot.py:223
-#pragma unroll
-        for (int d = 0; d < A1_DOF; ++d) {
-          h[12 + d] = clampf(sub_rn(s.dof[e][2 * d], k.q0[d]), -c, c);
-          h[24 + d] = clampf(s.dof[e][2 * d + 1], -c, c);
-        }
-        // HistoryRecorder.flatten (train.py:33-35): slot-major; then add() (train.py:12-14)
-#pragma unroll
-        for (int d = 0; d < A1_DOF; ++d) {
-          const float a0 = s.hist[e][d * A1_HIST + 0], a1 = s.hist[e][d * A1_HIST + 1],
-                      a2 = s.hist[e][d * A1_HIST + 2];
-          h[36 + d] = clampf(a0, -c, c);
-          h[48 + d] = clampf(a1, -c, c);
-          h[60 + d] = clampf(a2, -c, c);
-          s.hist[e][d * A1_HIST + 2] = a1;
-          s.hist[e][d * A1_HIST + 1] = a0;
-          s.hist[e][d * A1_HIST + 0] = s.act[e][d];
-        }
-        s.zb[e] = sub_rn(s.root[e][2], k.h_off);                          // post-reset base z
-        // -- carried body-frame velocities for the next control step (robot.py:222-229, D7)
-        if (io.carry_body_frame) {
-          float o[3];
-          rotate_inverse(&s.root[e][3], s.root[e][7], s.root[e][8], s.root[e][9], o);
-          io.base_lin_vel[ge * 3LL + 0] = o[0]; io.base_lin_vel[ge * 3LL + 1] = o[1];
-          io.base_lin_vel[ge * 3LL + 2] = o[2];
-          rotate_inverse(&s.root[e][3], s.root[e][10], s.root[e][11], s.root[e][12], o);
-          io.base_ang_vel[ge * 3LL + 0] = o[0]; io.base_ang_vel[ge * 3LL + 1] = o[1];
-          io.base_ang_vel[ge * 3LL + 2] = o[2];
-          rotate_inverse(&s.root[e][3], 0.0f, 0.0f, -1.0f, o);
-          io.projected_gravity[ge * 3LL + 0] = o[0]; io.projected_gravity[ge * 3LL + 1] = o[1];
-          io.projected_gravity[ge * 3LL + 2] = o[2];
-        }
-      }
-      a1_log_sums(k, reset, st_sum, level_delta, t);
-    }
-    __syncthreads();
-
-    // ---- phase C: 187-point scan; obs[., 72 + t] = clip((z - 0.5) - h, +-1) ----
-    if (t < A1_POINTS) {
-      float* orow = io.obs_buf + (long long)e0 * A1_OBS + A1_HEAD + t;
-      float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + (long long)e0 * A1_POINTS + t
-                                                     : nullptr;
-#pragma unroll 4
-      for (int e = 0; e < ne; ++e) {
-        unsigned px, py;
-        const float hgt = scan_point(s.ev[e], bx, by, k, &px, &py);
-        float v = clampf(sub_rn(s.zb[e], hgt), -k.h_clip, k.h_clip);
-        v = clampf(v, -k.clip_obs, k.clip_obs);
-        __stcs(orow + (long long)e * A1_OBS, v);
-        if (mrow != nullptr) __stcs(mrow + (long long)e * A1_POINTS, hgt);
-      }
-    }
-
-    // ---- phase D: obs head + history tile ----
-    {
-      float* obase = io.obs_buf + (long long)e0 * A1_OBS;
-      const float* hsrc = &s.head[0][0];
-      for (int i = t; i < ne * A1_HEAD; i += A1_THREADS) {
-        const int e = i / A1_HEAD, j = i - e * A1_HEAD;
-        __stcs(obase + (long long)e * A1_OBS + j, hsrc[i]);
-      }
-      store_span(io.history + (long long)e0 * (A1_DOF * A1_HIST), &s.hist[0][0], ne * A1_DOF * A1_HIST, t,
-                 A1_THREADS);
-    }
-    __syncthreads();   // smem is reused by the next tile of a grid-stride CTA
-  }
-}
-
 }  // namespace shifu

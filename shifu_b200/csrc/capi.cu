@@ -9,6 +9,7 @@
 
 #include "../../include/shifu_b200.h"
 #include "a1_kernels.cuh"
+#include "a1_fused.cuh"
 #include "abb_kernels.cuh"
 #include "common_kernels.cuh"
 
@@ -56,6 +57,7 @@ struct ShifuCtx {
   int chain_len = 0;
   unsigned epoch = 0;
   int a1_grid = 0;
+  int a1_occ = 0;
 };
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -142,14 +144,27 @@ static int fill_abbk(const ShifuAbbDesc& d, AbbK& k) {
   return SHIFU_OK;
 }
 
+static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc* abb, int util_envs, ShifuCtx** out);
+
 extern "C" int shifu_ctx_create(int device, const ShifuA1Desc* a1, const ShifuAbbDesc* abb, ShifuCtx** out) {
   REQUIRE_PTR(out);
   *out = nullptr;
   if ((a1 == nullptr) == (abb == nullptr)) return fail(SHIFU_E_NULL, "exactly one of a1 / abb must be given");
+  return ctx_create_impl(device, a1, abb, 0, out);
+}
+
+extern "C" int shifu_ctx_create_util(int device, int32_t num_envs, ShifuCtx** out) {
+  REQUIRE_PTR(out);
+  *out = nullptr;
+  if (num_envs <= 0) return fail(SHIFU_E_RANGE, "num_envs must be > 0 (got %d)", num_envs);
+  return ctx_create_impl(device, nullptr, nullptr, num_envs, out);
+}
+
+static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc* abb, int util_envs, ShifuCtx** out) {
   // validate the descriptor before touching the device so argument errors surface without a GPU
   A1K a1k; AbbK abbk;
   if (a1 != nullptr) { int rc = fill_a1k(*a1, a1k); if (rc) return rc; }
-  else { int rc = fill_abbk(*abb, abbk); if (rc) return rc; }
+  else if (abb != nullptr) { int rc = fill_abbk(*abb, abbk); if (rc) return rc; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     cudaGetLastError();
@@ -166,7 +181,8 @@ extern "C" int shifu_ctx_create(int device, const ShifuA1Desc* a1, const ShifuAb
   c->sm_count = prop.multiProcessorCount;
   int n = 0;
   if (a1 != nullptr) { c->is_a1 = true; c->a1 = *a1; c->a1k = a1k; n = a1->num_envs; }
-  else { c->is_abb = true; c->abb = *abb; c->abbk = abbk; n = abb->num_envs; }
+  else if (abb != nullptr) { c->is_abb = true; c->abb = *abb; c->abbk = abbk; n = abb->num_envs; }
+  else n = util_envs;
   cudaError_t e = cudaMalloc(&c->d_stats, sizeof(double) * (SHIFU_NUM_STATS + 1));
   if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, sizeof(double) * (SHIFU_NUM_STATS + 1));
   c->chain_len = (n + COMPACT_CHUNK - 1) / COMPACT_CHUNK + 1;
@@ -175,11 +191,20 @@ extern "C" int shifu_ctx_create(int device, const ShifuA1Desc* a1, const ShifuAb
   if (e == cudaSuccess) e = cudaMalloc(&c->d_ticket, sizeof(unsigned) * 2);
   if (e == cudaSuccess) e = cudaMemset(c->d_ticket, 0, sizeof(unsigned) * 2);
   if (e == cudaSuccess && c->is_a1) {
+    // all four instantiations share resources; ask for the full shared-memory carve-out so the
+    // resident-CTA count is bounded by registers/threads, not by the default L1/smem split
+    const void* variants[4] = {
+        (const void*)a1_post_physics_kernel<true, false>, (const void*)a1_post_physics_kernel<true, true>,
+        (const void*)a1_post_physics_kernel<false, false>, (const void*)a1_post_physics_kernel<false, true>};
+    for (int v = 0; v < 4 && e == cudaSuccess; ++v)
+      e = cudaFuncSetAttribute(variants[v], cudaFuncAttributePreferredSharedMemoryCarveout, 75);
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, a1_post_physics_kernel, A1_THREADS, sizeof(A1Smem));
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, a1_post_physics_kernel<true, false>, A1_THREADS, 0);
     const int tiles = (n + A1_TILE - 1) / A1_TILE;
     const int cap = c->sm_count * (occ > 0 ? occ : 1);
     c->a1_grid = tiles < cap ? tiles : cap;
+    c->a1_occ = occ;
   }
   if (e != cudaSuccess) {
     int rc = fail((int)e, "shifu_ctx_create: %s", cudaGetErrorString(e));
@@ -245,10 +270,12 @@ extern "C" int shifu_set_level_sum(ShifuCtx* c, const int64_t* levels, void* str
 extern "C" int shifu_pd_torque(ShifuCtx* c, const float* a_in, float* a_out, const float* dof, float* tau, void* stream) {
   REQUIRE_PTR(c); REQUIRE_PTR(a_in); REQUIRE_PTR(dof); REQUIRE_PTR(tau);
   if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_pd_torque needs an A1 ctx");
-  REQUIRE_ALIGNED(dof, 8);
-  const long long total = (long long)c->a1.num_envs * A1_DOF;
-  pd_torque_kernel<<<grid_for(total, 256, c->sm_count, 8), 256, 0, S(stream)>>>(
-      c->a1k, a_in, a_out, reinterpret_cast<const float2*>(dof), tau);
+  REQUIRE_ALIGNED(dof, 16); REQUIRE_ALIGNED(a_in, 16); REQUIRE_ALIGNED(tau, 16);
+  if (a_out != nullptr) REQUIRE_ALIGNED(a_out, 16);
+  const long long quads = (long long)c->a1.num_envs * (A1_DOF / 4);
+  pd_torque_kernel<<<grid_for(quads, 256, c->sm_count, 8), 256, 0, S(stream)>>>(
+      c->a1k, reinterpret_cast<const float4*>(a_in), reinterpret_cast<float4*>(a_out),
+      reinterpret_cast<const float4*>(dof), reinterpret_cast<float4*>(tau));
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }
@@ -286,7 +313,12 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
   for (int j = 0; j < c->a1.num_reward_terms; ++j)
     if (io->ep_sums[j] == nullptr) return fail(SHIFU_E_NULL, "ep_sums[%d] is NULL", j);
   REQUIRE_ALIGNED(io->dof_state, 16);
-  a1_post_physics_kernel<<<c->a1_grid, A1_THREADS, sizeof(A1Smem), S(stream)>>>(c->a1k, *io);
+  const dim3 grid(c->a1_grid), block(A1_THREADS);
+  const bool tiled = c->a1k.tiled != 0, exact = c->a1k.exact_div != 0;
+  if (tiled && !exact) a1_post_physics_kernel<true, false><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
+  else if (tiled && exact) a1_post_physics_kernel<true, true><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
+  else if (!tiled && !exact) a1_post_physics_kernel<false, false><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
+  else a1_post_physics_kernel<false, true><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }
