@@ -84,7 +84,7 @@ def _terrain():
     from shifu_b200.sim import fake_isaacgym
     fake_isaacgym.install("cpu")
     from shifu_b200.configs import TerrainEnvConfig
-    from shifu_b200.utils.terrain import Terrain
+    from shifu_b200.utils.heightmap import Terrain
     np.random.seed(0)
     cfg = TerrainEnvConfig()
     return Terrain(cfg.terrain, 1), cfg

@@ -240,7 +240,9 @@ int shifu_pd_torque(ShifuCtx* ctx, const float* actions_in, float* actions_out, 
                     float* torques, void* stream);
 
 /* ---- row a3: LeggedRobot.post_step (shifu/units/robot.py:222-229) -------------------------- */
-int shifu_body_frame(ShifuCtx* ctx, const float* root_state, float* base_lin_vel, float* base_ang_vel,
+/* Root row of env e = root_state[(root_offset + e*root_stride)*13 ..]; works on any ctx. */
+int shifu_body_frame(ShifuCtx* ctx, const float* root_state, int32_t num_envs, int32_t root_stride,
+                     int32_t root_offset, float* base_lin_vel, float* base_ang_vel,
                      float* projected_gravity, float* gravity_vec, void* stream);
 
 /* ---- row a5: TerrainGymEnv.get_heights (shifu/gym/isaac_gym.py:393-433) --------------------

@@ -330,6 +330,9 @@ def a1_reset_idx(p: A1Params, st: A1State, env_ids):
     st.reset[env_ids] = 1
     st.history.index_fill_(0, env_ids, 0.)                  # shifu/utils/train.py:16-17
     st.extras["episode"] = {}
+    # un-normalised sums of this reset (what a sharded run all-reduces)
+    st.extras["_stats"] = {"sums": [float(st.ep_sums[k][env_ids].double().sum()) for k in st.ep_sums],
+                           "n_reset": int(len(env_ids)), "level_sum": int(st.terrain_levels.sum()), "n_envs": p.n}
     for key in st.ep_sums.keys():                           # log_info env.py:149-153
         st.extras["episode"][key] = torch.mean(st.ep_sums[key][env_ids]) / p.max_episode_length_s
         st.ep_sums[key][env_ids] = 0.

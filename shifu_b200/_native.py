@@ -106,7 +106,7 @@ SIGNATURES = {
     "shifu_set_height_map": [_VP, _VP, _I32, _I32, _VP],
     "shifu_set_level_sum": [_VP, _VP, _VP],
     "shifu_pd_torque": [_VP, _VP, _VP, _VP, _VP, _VP],
-    "shifu_body_frame": [_VP, _VP, _VP, _VP, _VP, _VP, _VP],
+    "shifu_body_frame": [_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP],
     "shifu_get_heights": [_VP, _VP, _VP, _VP, _VP],
     "shifu_a1_post_physics": [_VP, C.POINTER(A1StepIO), _VP],
     "shifu_abb_post_physics": [_VP, C.POINTER(AbbStepIO), _VP],

@@ -154,10 +154,10 @@ __device__ __forceinline__ void rotate_inverse(const float* q, float vx, float v
 // Row a3: LeggedRobot.post_step (shifu/units/robot.py:222-229), one thread per env.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-body_frame_kernel(const __grid_constant__ A1K k, const float* __restrict__ root, float* __restrict__ lin,
+body_frame_kernel(int n, int root_stride, int root_offset, const float* __restrict__ root, float* __restrict__ lin,
                   float* __restrict__ ang, float* __restrict__ pg, float* __restrict__ gvec) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k.n; e += gridDim.x * blockDim.x) {
-    const float* r = root + ((long long)e * k.root_stride + k.root_offset) * 13;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const float* r = root + ((long long)e * root_stride + root_offset) * 13;
     float row[13];
 #pragma unroll
     for (int j = 0; j < 13; ++j) row[j] = r[j];

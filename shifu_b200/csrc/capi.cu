@@ -280,10 +280,13 @@ extern "C" int shifu_pd_torque(ShifuCtx* c, const float* a_in, float* a_out, con
   return SHIFU_OK;
 }
 
-extern "C" int shifu_body_frame(ShifuCtx* c, const float* root, float* lin, float* ang, float* pg, float* gvec, void* stream) {
+extern "C" int shifu_body_frame(ShifuCtx* c, const float* root, int32_t n, int32_t root_stride, int32_t root_offset,
+                                float* lin, float* ang, float* pg, float* gvec, void* stream) {
   REQUIRE_PTR(c); REQUIRE_PTR(root); REQUIRE_PTR(lin); REQUIRE_PTR(ang); REQUIRE_PTR(pg);
-  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_body_frame needs an A1 ctx");
-  body_frame_kernel<<<grid_for(c->a1.num_envs, 256, c->sm_count, 8), 256, 0, S(stream)>>>(c->a1k, root, lin, ang, pg, gvec);
+  if (n <= 0 || root_stride < 1 || root_offset < 0 || root_offset >= root_stride)
+    return fail(SHIFU_E_RANGE, "shifu_body_frame: n=%d stride=%d offset=%d invalid", n, root_stride, root_offset);
+  body_frame_kernel<<<grid_for(n, 256, c->sm_count, 8), 256, 0, S(stream)>>>(n, root_stride, root_offset, root, lin,
+                                                                            ang, pg, gvec);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }

@@ -124,8 +124,76 @@ class _Ctx:
             pass
 
 
+class EnvKernels:
+    """Task-independent rows for envs whose hooks stay user-written torch code: reset-id
+    compaction (a8), history push (a13), clip (a14), body-frame velocities (a3)."""
+
+    def __init__(self, device, num_envs: int):
+        self.lib = nv.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nv.ShifuNativeError(nv.E_NODEVICE, f"device {device} is not CUDA: the shifu_b200 kernels "
+                                                     "have no CPU fallback")
+        self.n = num_envs
+        self.handle = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        nv.check(self.lib.shifu_ctx_create_util(idx, num_envs, C.byref(self.handle)))
+        self._ids = torch.zeros(num_envs, device=self.device, dtype=torch.long)
+        self._cnt = torch.zeros(1, device=self.device, dtype=torch.int32)
+
+    def __del__(self):
+        try:
+            if self.handle.value:
+                self.lib.shifu_ctx_destroy(self.handle)
+        except Exception:
+            pass
+
+    def nonzero(self, flags: torch.Tensor) -> torch.Tensor:
+        """``flags.nonzero().flatten()`` (env.py:101): ascending int64 ids.  Synchronises to learn
+        the length, like the reference's ``nonzero`` does."""
+        f = flags if flags.dtype in (torch.bool, torch.uint8) else (flags != 0)
+        f = f.contiguous()
+        nv.check(self.lib.shifu_compact_reset_ids(self.handle, nv.ptr(f), f.numel(), nv.ptr(self._ids),
+                                                  nv.ptr(self._cnt), nv.current_stream()))
+        return self._ids[: int(self._cnt.item())].clone()
+
+    def history_add(self, history_buf: torch.Tensor, x: torch.Tensor):
+        n, a, h = history_buf.shape
+        nv.check(self.lib.shifu_history_add(self.handle, nv.ptr(history_buf), nv.ptr(x.contiguous()), n, a, h,
+                                            nv.current_stream()))
+
+    def clip(self, x: torch.Tensor, c: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = x.contiguous()
+        out = torch.empty_like(x) if out is None else out
+        nv.check(self.lib.shifu_clip(self.handle, nv.ptr(x), nv.ptr(out), x.numel(), float(c), nv.current_stream()))
+        return out
+
+    def body_frame(self, root_state, n, stride, offset, lin, ang, pg, gvec=None):
+        nv.check(self.lib.shifu_body_frame(self.handle, nv.ptr(root_state), n, stride, offset, nv.ptr(lin),
+                                           nv.ptr(ang), nv.ptr(pg), nv.ptr(gvec), nv.current_stream()))
+
+
+class HeightScan:
+    """Stand-alone row a5 (``TerrainGymEnv.get_heights``) for user-hook tasks."""
+
+    def __init__(self, desc: nv.A1Desc, height_samples: torch.Tensor, root_state: torch.Tensor):
+        self.ctx = _Ctx(root_state.device, a1=desc)
+        self.lib = self.ctx.lib
+        self.root_state = root_state
+        self.height_samples = height_samples.contiguous()
+        self.out = torch.zeros(desc.num_envs, desc.num_points_x * desc.num_points_y, device=root_state.device)
+        nv.check(self.lib.shifu_set_height_map(self.ctx.handle, nv.ptr(self.height_samples),
+                                               self.height_samples.shape[0], self.height_samples.shape[1],
+                                               nv.current_stream()))
+
+    def run(self, cell_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        nv.check(self.lib.shifu_get_heights(self.ctx.handle, nv.ptr(self.root_state), nv.ptr(self.out),
+                                            nv.ptr(cell_idx), nv.current_stream()))
+        return self.out
+
+
 class A1HotPath:
-    """Fused A1 step.  ``root_state`` / ``dof_state`` / ``contact_state`` are the gym's flat tensors."""
+    """Fused A1 step. ``root_state`` / ``dof_state`` / ``contact_state`` are the gym's flat tensors."""
 
     def __init__(self, desc: nv.A1Desc, *, root_state, dof_state, contact_state, height_samples,
                  terrain_origins, terrain_types, env_origins, terms: Sequence[str] = tuple(A1_TERM_CODES),
@@ -228,9 +296,11 @@ class A1HotPath:
 
     def body_frame(self):
         """Row a3: LeggedRobot.post_step on the CURRENT content of root_state (S_prev, D7)."""
-        nv.check(self.lib.shifu_body_frame(self.ctx.handle, nv.ptr(self.root_state), nv.ptr(self.base_lin_vel),
-                                           nv.ptr(self.base_ang_vel), nv.ptr(self.projected_gravity),
-                                           nv.ptr(self.gravity_vec), nv.current_stream()))
+        nv.check(self.lib.shifu_body_frame(self.ctx.handle, nv.ptr(self.root_state), self.n,
+                                           self.desc.root_stride, self.desc.root_offset,
+                                           nv.ptr(self.base_lin_vel), nv.ptr(self.base_ang_vel),
+                                           nv.ptr(self.projected_gravity), nv.ptr(self.gravity_vec),
+                                           nv.current_stream()))
 
     def get_heights(self, out: Optional[torch.Tensor] = None, cell_idx: Optional[torch.Tensor] = None):
         """Row a5 stand-alone."""

@@ -215,6 +215,9 @@ class FakeEnv:
 class FakeGym:
     """Implements the subset of ``gymapi.Gym`` reached from the hot path's callers."""
 
+    # the stand-in keeps no hidden simulator state: rows rewritten in place need no indexed setter
+    needs_indexed_resets = False
+
     def __init__(self):
         self.sims: List[FakeSim] = []
 

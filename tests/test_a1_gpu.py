@@ -22,7 +22,7 @@ def _terrain(n):
     from shifu_b200.sim import fake_isaacgym
     fake_isaacgym.install("cpu")
     from shifu_b200.configs import TerrainEnvConfig
-    from shifu_b200.utils.terrain import Terrain
+    from shifu_b200.utils.heightmap import Terrain
     np.random.seed(0)
     cfg = TerrainEnvConfig()
     ter = Terrain(cfg.terrain, n)

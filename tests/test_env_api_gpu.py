@@ -1,0 +1,128 @@
+"""GPU tests of the drop-in class API (ShifuVecEnv / Unit mirror + tasks) on the stand-in simulator:
+the same call sequence the reference harness used to record the golden fixtures
+(env.reset(), then env.step(actions) with replayed simulator snapshots)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _install():
+    from shifu_b200.sim import fake_isaacgym
+    fake_isaacgym.install("cuda:0")
+    fake_isaacgym.reset_gym()
+    fake_isaacgym.set_default_device("cuda:0")
+    return fake_isaacgym
+
+
+def _make_a1(n, terrain, fused=True, carry=False):
+    _install()
+    from shifu_b200.tasks.a1_conditional import A1Conditional, A1EnvConfig
+    cfg = A1EnvConfig()
+    cfg.num_envs = n
+    cfg.device = "cuda:0"
+    for k, v in (terrain or {}).items():
+        setattr(cfg.terrain, k, v)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    return A1Conditional(cfg, fused=fused, carry_body_frame=carry)
+
+
+def _env_outputs(env):
+    isg, rb = env.isg_env, env.robot
+    d = dict(obs=env.obs_buf, rew=env.rew_buf, reset=env.reset_buf.to(torch.uint8),
+             time_out=env.time_out_buf.to(torch.uint8), contact_term=env.contact_terminate_buf.to(torch.uint8),
+             ep_len=env.episode_length_buf, terrain_levels=env.terrain_levels, env_origins=isg.env_origins,
+             command=env.command_buf, history=env.actions_recorder.history_buf, actions=env.actions,
+             root_state=isg.root_state, dof_state=isg.dof_state, dof_targets=rb.dof_targets,
+             rand_force=rb.rand_force_buf, torques=rb.torques, base_lin_vel=rb.base_lin_vel,
+             base_ang_vel=rb.base_ang_vel, projected_gravity=rb.projected_gravity,
+             measured_heights=isg.measured_heights)
+    for k, v in env.episode_rewards.items():
+        d["ep_sum/" + k] = v
+    for k, v in env.extras.get("episode", {}).items():
+        d["extras/" + k] = torch.as_tensor(v)
+    return {k: v.detach().cpu().numpy().copy() for k, v in d.items()}
+
+
+@pytest.mark.parametrize("fused,carry", [(True, False), (True, True), (False, False)])
+def test_a1_class_api_replays_golden(fused, carry):
+    from shifu_b200.sim.synthetic import A1Replay
+    z, meta = util.load_golden("a1_small")
+    n = meta["n"]
+    env = _make_a1(n, meta["terrain"], fused=fused, carry=carry)
+    isg = env.isg_env
+    assert np.array_equal(isg.height_samples.cpu().numpy(), z["height_samples"])
+    assert np.array_equal(isg.env_origins.cpu().numpy(), z["env_origins_init"])
+    assert np.array_equal(isg.terrain_types.cpu().numpy(), z["terrain_types"])
+
+    class Replay(A1Replay):              # serve the fixture's recorded snapshots
+        def begin_step(self, step):
+            self.snap = util.golden_snap(z, step)
+            self._dof_i = 0
+            self.enabled = True
+            return self.snap.actions
+
+    replay = Replay(0, n, lambda: isg.env_origins)
+    isg.sim.provider = replay
+    skip = ("base_lin_vel", "base_ang_vel", "projected_gravity") if carry else ()
+    replay.begin_step(0)
+    env.reset()
+    util.compare_a1(_env_outputs(env), util.golden_out(z, 0), "api/reset", skip=skip)
+    env.episode_length_buf = torch.from_numpy(z["ep_len_init"]).cuda()       # rsl_rl-style re-binding
+    env.terrain_levels[:] = torch.from_numpy(z["levels_init"]).cuda()
+    if fused:
+        env.hot.sync_level_sum()
+    for t in range(1, meta["steps"] + 1):
+        actions = replay.begin_step(t)
+        obs, priv, rew, dones, extras = env.step(actions.cuda())
+        assert priv is None and obs.shape == (n, 259) and dones.dtype == torch.bool
+        util.compare_a1(_env_outputs(env), util.golden_out(z, t), f"api/s{t}", skip=skip)
+        assert torch.equal(extras["time_outs"].cpu(), torch.from_numpy(z[f"s{t}/out/time_out"]).bool())
+
+
+def test_abb_class_api_replays_golden():
+    _install()
+    from shifu_b200.sim.synthetic import AbbReplay
+    from shifu_b200.tasks.abb_pushbox import AbbPushBox, PriorStageEnvConfig
+    z, meta = util.load_golden("abb_small")
+    n = meta["n"]
+    cfg = PriorStageEnvConfig()
+    cfg.num_envs = n
+    cfg.device = "cuda:0"
+    env = AbbPushBox(cfg, rng_seed=meta["rng_seed"])
+
+    class Replay(AbbReplay):
+        def begin_step(self, step):
+            self.snap = util.golden_snap(z, step, "abb")
+            self.enabled = True
+            return self.snap.actions
+
+    replay = Replay(0, n)
+    env.isg_env.sim.provider = replay
+    env.episode_length_buf = torch.from_numpy(z["ep_len_init"]).cuda()
+    for t in range(1, meta["steps"] + 1):
+        actions = replay.begin_step(t)
+        obs, _, rew, dones, extras = env.step(actions.cuda())
+        want = util.golden_out(z, t)
+        got = dict(obs=obs, rew=rew, reset=dones.to(torch.uint8), time_out=env.time_out_buf.to(torch.uint8),
+                   success=env.success_buf.to(torch.uint8), ep_len=env.episode_length_buf,
+                   root_state=env.isg_env.root_state, dof_state=env.isg_env.dof_state)
+        for k, v in env.episode_rewards.items():
+            got["ep_sum/" + k] = v
+        for k, v in extras["episode"].items():
+            got["extras/" + k] = v
+        got = {k: v.detach().cpu().numpy() for k, v in got.items()}
+        util.compare_a1(got, want, f"abb api/s{t}", skip=("dof_targets",))
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly off-GPU (ShifuNativeError), never fall back to torch."""
+    from shifu_b200 import _native as nv, hotpath
+    with pytest.raises(nv.ShifuNativeError):
+        hotpath.EnvKernels("cpu", 16)
+    with pytest.raises(nv.ShifuNativeError):
+        nv.ptr(torch.zeros(4))

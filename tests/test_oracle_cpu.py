@@ -46,7 +46,7 @@ def _replay_a1(name, regenerate_map):
         from shifu_b200.sim import fake_isaacgym
         fake_isaacgym.install("cpu")
         from shifu_b200.configs import TerrainEnvConfig
-        from shifu_b200.utils.terrain import Terrain
+        from shifu_b200.utils.heightmap import Terrain
         import hashlib
         np.random.seed(meta["map_seed"])
         ter = Terrain(TerrainEnvConfig().terrain, n)
