@@ -1,0 +1,393 @@
+// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs with three warp
+// roles that never meet at a CTA-wide barrier —
+//
+//   DMA warp (1 lane)   bulk-TMA loads of the next tiles' root/dof/contact/history/torque/action
+//                       rows (cp.async.bulk -> mbarrier), bulk-TMA stores of the finished obs tile
+//                       (32 x 259 floats, one 33 KB copy) and of the pushed history tile
+//   B group (2 warps)   lane = env: termination, reward terms + episode sums, reset (curriculum,
+//                       Philox, state rewrite), obs head, history push, carried body-frame —
+//                       the scalar "game logic" of ShifuVecEnv.post_step (env.py:93-106)
+//   C group (6 warps)   thread = scan point: the 187-point height scan of every env of the tile
+//                       (isaac_gym.py:393-433) written into the shared obs tile
+//
+// Tiles are double-buffered in shared memory; mbarriers hand buffers round
+// DMA -> B -> C -> DMA, so B works one to two tiles ahead of C and the global loads/stores of
+// neighbouring tiles overlap both.  Every HBM byte moves through the TMA engine in 128-byte
+// bursts; the SM only issues arithmetic, shared-memory accesses and the L1/L2 table gathers.
+#pragma once
+#include "a1_fused.cuh"
+#include "f32x2.cuh"
+#include "tma_pipe.cuh"
+
+namespace shifu {
+
+constexpr int V3_B_THREADS = 64, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
+constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;   // 288
+
+struct alignas(128) V3In {            // one tile of simulator/env rows, each member 16-B aligned
+  float root[A1_TILE][13];            //  1664 B
+  float dof[A1_TILE][A1_DOF * 2];     //  3072 B
+  float contact[A1_TILE][A1_BODIES * 3];   // 6528 B
+  float hist[A1_TILE][A1_DOF * A1_HIST];   // 4608 B  (pushed in place, then bulk-stored back)
+  float tau[A1_TILE][A1_DOF];         //  1536 B
+  float act[A1_TILE][A1_DOF];         //  1536 B
+};
+static_assert(sizeof(V3In) == 18944, "tile layout");
+
+struct alignas(128) V3Smem {
+  V3In in[2];
+  float out[2][A1_TILE][A1_OBS];      // obs tiles, 33152 B each
+  // per-env scan scalars, laid out per env PAIR (e, e+1) so that one 128-bit broadcast load yields
+  // two packed fp32x2 operands: sA = (2zq_e, 2zq_e1, zq_e, zq_e1), sB = (wq_e, wq_e1, x_e, x_e1),
+  // sC = (y_e, y_e1, zb_e, zb_e1); (zq, wq) = normalised yaw quaternion of the PRE-reset pose,
+  // zb = z_postreset - 0.5
+  float4 sA[2][A1_TILE / 2];
+  float4 sB[2][A1_TILE / 2];
+  float4 sC[2][A1_TILE / 2];
+  float rterm[SHIFU_MAX_REWARD_TERMS][A1_TILE];
+  float cla[A1_TILE][9];
+  uint64_t full_in[2], b_done[2], c_done[2], free_buf[2];
+};
+
+constexpr uint32_t V3_IN_BYTES = sizeof(V3In);
+constexpr uint32_t V3_OUT_BYTES = A1_TILE * A1_OBS * 4;
+constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
+
+__device__ __forceinline__ void v3_issue_loads(V3In& in, const ShifuA1StepIO& io, long long e0, uint64_t* bar) {
+  pipe::mbar_arrive_expect_tx(bar, V3_IN_BYTES);
+  pipe::bulk_load(in.root, io.root_state + e0 * 13, sizeof(in.root), bar);
+  pipe::bulk_load(in.dof, io.dof_state + e0 * (A1_DOF * 2), sizeof(in.dof), bar);
+  pipe::bulk_load(in.contact, io.contact_state + e0 * (A1_BODIES * 3), sizeof(in.contact), bar);
+  pipe::bulk_load(in.hist, io.history + e0 * (A1_DOF * A1_HIST), sizeof(in.hist), bar);
+  pipe::bulk_load(in.tau, io.torques + e0 * A1_DOF, sizeof(in.tau), bar);
+  pipe::bulk_load(in.act, io.actions + e0 * A1_DOF, sizeof(in.act), bar);
+}
+
+// Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
+__device__ __noinline__ float v3_eval_term(int code, float p0, float p1, const A1K& k, const V3In& in,
+                                           const float* cla, int e) {
+  switch (code) {
+    case SHIFU_REW_TRACKING_LIN_VEL: {
+      const float dx = sub_rn(cla[0], cla[3]), dy = sub_rn(cla[1], cla[4]);
+      return mul_rn(p0, expf(div_rn(-add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), p1)));
+    }
+    case SHIFU_REW_TRACKING_ANG_VEL: {
+      const float d = sub_rn(cla[2], cla[8]);
+      return mul_rn(p0, expf(div_rn(-mul_rn(d, d), p1)));
+    }
+    case SHIFU_REW_STABILIZING_BASE:
+      return add_rn(mul_rn(p0, mul_rn(cla[5], cla[5])),
+                    mul_rn(p1, add_rn(mul_rn(cla[6], cla[6]), mul_rn(cla[7], cla[7]))));
+    case SHIFU_REW_SMOOTHING_ACTION: {
+      float f1 = 0.0f, f2 = 0.0f;
+#pragma unroll
+      for (int d = 0; d < A1_DOF; ++d) {
+        const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
+                    a2 = in.hist[e][d * A1_HIST + 2];
+        const float d1 = sub_rn(a1, a0);
+        const float d2 = add_rn(sub_rn(a2, mul_rn(2.0f, a1)), a0);
+        f1 = add_rn(f1, mul_rn(d1, d1));
+        f2 = add_rn(f2, mul_rn(d2, d2));
+      }
+      return mul_rn(p0, add_rn(f1, f2));
+    }
+    case SHIFU_REW_LEG_COLLISION: {
+      int cnt = 0;
+      for (int b = 0; b < k.n_leg; ++b) {
+        const float* f = &in.contact[e][k.leg[b] * 3];
+        cnt += (norm3_fma(f[0], f[1], f[2]) > p1) ? 1 : 0;
+      }
+      return mul_rn(p0, (float)cnt);
+    }
+    case SHIFU_REW_TORQUES: {
+      float acc = 0.0f;
+#pragma unroll
+      for (int d = 0; d < A1_DOF; ++d) acc = add_rn(acc, mul_rn(in.tau[e][d], in.tau[e][d]));
+      return mul_rn(p0, acc);
+    }
+    default:
+      return 0.0f;
+  }
+}
+
+// Processes tiles [0, num_tiles) of 32 envs each (the ragged tail, if any, is a separate launch of
+// the barrier-phased kernel).  Requires root_stride == 1 and 16-byte aligned tensors.
+template <bool TILED, bool EXACT_DIV>
+__global__ void __launch_bounds__(V3_THREADS, 2)
+a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io, int num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  V3Smem& s = *reinterpret_cast<V3Smem*>(smem_raw);
+  const int t = threadIdx.x;
+  const long long step = (io.step_dev != nullptr) ? *io.step_dev : io.step;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = (first < num_tiles) ? (num_tiles - first + stride - 1) / stride : 0;
+
+  if (t == 0) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      pipe::mbar_init(&s.full_in[b], 1);
+      pipe::mbar_init(&s.b_done[b], 1);
+      pipe::mbar_init(&s.c_done[b], 1);
+      pipe::mbar_init(&s.free_buf[b], 1);
+    }
+    pipe::fence_barrier_init();
+  }
+  __syncthreads();
+
+  // =========================================================================================
+  if (t >= V3_B_THREADS + V3_C_THREADS) {
+    // ---------------- DMA warp ----------------
+    if (t != V3_B_THREADS + V3_C_THREADS) return;
+    for (int j = 0; j < 2 && j < my_tiles; ++j)
+      v3_issue_loads(s.in[j], io, (long long)(first + j * stride) * A1_TILE, &s.full_in[j]);
+    for (int j = 0; j < my_tiles; ++j) {
+      const int b = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      const long long e0 = (long long)(first + j * stride) * A1_TILE;
+      pipe::mbar_wait(&s.b_done[b], par);                     // history pushed, head written
+      pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
+      pipe::bulk_commit();
+      pipe::mbar_wait(&s.c_done[b], par);                     // heights written
+      pipe::bulk_store(io.obs_buf + e0 * A1_OBS, s.out[b], V3_OUT_BYTES);
+      pipe::bulk_commit();
+      pipe::bulk_wait_read_all();                             // smem of this buffer is reusable
+      if (j + 2 < my_tiles)
+        v3_issue_loads(s.in[b], io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
+      pipe::mbar_arrive(&s.free_buf[b]);
+    }
+    pipe::bulk_wait_all();                                    // global writes done before exit
+    return;
+  }
+
+  if (t < V3_B_THREADS) {
+    // ---------------- B group: lane = env ----------------
+    const int warp = t >> 5, lane = t & 31;
+    long long len_n = 0;
+    float c9_n[9], es_n[SHIFU_MAX_REWARD_TERMS];
+    // software-pipelined per-env scalars (warp 0 only): loaded one tile ahead
+    auto prefetch = [&](int j) {
+      const long long ge = (long long)(first + j * stride) * A1_TILE + lane;
+      len_n = io.ep_len[ge];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        c9_n[q] = io.command[ge * 3 + q];
+        c9_n[3 + q] = io.base_lin_vel[ge * 3 + q];
+        c9_n[6 + q] = io.base_ang_vel[ge * 3 + q];
+      }
+#pragma unroll
+      for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) es_n[q] = (q < k.n_terms) ? io.ep_sums[q][ge] : 0.0f;
+    };
+    if (warp == 0 && my_tiles > 0) prefetch(0);
+
+    for (int j = 0; j < my_tiles; ++j) {
+      const int b = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      const long long e0 = (long long)(first + j * stride) * A1_TILE;
+      const long long ge = e0 + lane;
+      V3In& in = s.in[b];
+      long long len = len_n;
+      float esum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+      for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) esum[q] = es_n[q];
+      if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) s.cla[lane][q] = c9_n[q];
+        if (j + 1 < my_tiles) prefetch(j + 1);
+      }
+      if (j >= 2) pipe::mbar_wait(&s.free_buf[b], par ^ 1);   // out/ev/pos of tile j-2 consumed
+      pipe::mbar_wait(&s.full_in[b], par);                    // tile rows have landed
+      pipe::named_barrier(1, V3_B_THREADS);                   // cla visible to both warps
+
+      // ---- B1: reward terms (warp w takes terms w, w+2, ...), termination, yaw normalisation
+      bool contact_term = false;
+#pragma unroll 1
+      for (int q = warp; q < k.n_terms; q += 2)
+        s.rterm[q][lane] = v3_eval_term(k.terms[q], k.rp[q][0], k.rp[q][1], k, in, s.cla[lane], lane);
+      if (warp == 0) {                                                    // a1_conditional.py:146-148
+        const float* fb = &in.contact[lane][k.base_body * 3];
+        contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
+      } else {
+        // heights are measured at the PRE-reset pose (isaac_gym.py:320-322 runs before post_step)
+        const ScanEnv ev = make_scan_env(in.root[lane]);
+        const int q = lane >> 1, sl = lane & 1;
+        float* a = reinterpret_cast<float*>(&s.sA[b][q]);
+        float* bb = reinterpret_cast<float*>(&s.sB[b][q]);
+        float* cc = reinterpret_cast<float*>(&s.sC[b][q]);
+        a[sl] = ev.z2; a[2 + sl] = ev.z;
+        bb[sl] = ev.w; bb[2 + sl] = ev.x;
+        cc[sl] = ev.y;
+      }
+      pipe::named_barrier(1, V3_B_THREADS);
+
+      // ---- B2: warp 0 — ordered accumulation, flags, reset, log sums
+      if (warp == 0) {
+        double st_sum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+        for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) st_sum[q] = 0.0;
+        long long level_delta = 0;
+        len += 1;                                                          // env.py:95
+        const bool time_out = len > k.max_len;                             // a1_conditional.py:149
+        const bool reset = contact_term | time_out;
+        float rew = 0.0f;                                                  // env.py:180-185
+#pragma unroll
+        for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) {
+          if (q < k.n_terms) {
+            const float r = s.rterm[q][lane];
+            esum[q] = add_rn(esum[q], r);
+            rew = add_rn(rew, r);
+          }
+        }
+        io.rew_buf[ge] = rew;
+        io.reset_buf[ge] = reset ? 1 : 0;
+        io.time_out_buf[ge] = time_out ? 1 : 0;
+        io.contact_term_buf[ge] = contact_term ? 1 : 0;
+        if (reset) {                                                       // env.py:101-102
+          float cmd[3] = {s.cla[lane][0], s.cla[lane][1], s.cla[lane][2]};
+          a1_reset_env<true>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
+                             st_sum, level_delta);
+          s.cla[lane][0] = cmd[0]; s.cla[lane][1] = cmd[1]; s.cla[lane][2] = cmd[2];
+        }
+        io.ep_len[ge] = len;
+#pragma unroll
+        for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q)
+          if (q < k.n_terms) io.ep_sums[q][ge] = esum[q];
+        reinterpret_cast<float*>(&s.sC[b][lane >> 1])[2 + (lane & 1)] =
+            sub_rn(in.root[lane][2], k.h_off);                              // post-reset base z (D8)
+        a1_log_sums(k, reset, st_sum, level_delta, lane);
+      }
+      pipe::named_barrier(1, V3_B_THREADS);
+
+      // ---- B3: obs head (a1_conditional.py:131-144), history push (train.py:12-14), carry
+      {
+        const float c = k.clip_obs;
+        for (int i = t; i < A1_TILE * A1_DOF; i += V3_B_THREADS) {
+          const int e = i / A1_DOF, d = i - e * A1_DOF;
+          float* h = s.out[b][e];
+          h[12 + d] = clampf(sub_rn(in.dof[e][2 * d], k.q0[d]), -c, c);
+          h[24 + d] = clampf(in.dof[e][2 * d + 1], -c, c);
+          const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
+                      a2 = in.hist[e][d * A1_HIST + 2];
+          h[36 + d] = clampf(a0, -c, c);               // HistoryRecorder.flatten: slot-major
+          h[48 + d] = clampf(a1, -c, c);
+          h[60 + d] = clampf(a2, -c, c);
+          in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
+          in.hist[e][d * A1_HIST + 1] = a0;
+          in.hist[e][d * A1_HIST + 0] = in.act[e][d];
+        }
+        for (int i = t; i < A1_TILE * 12; i += V3_B_THREADS) {
+          const int e = i / 12, q = i - e * 12;
+          const float v = (q < 9) ? s.cla[e][q] : ((q == 11) ? -1.0f : 0.0f);
+          s.out[b][e][q] = clampf(v, -c, c);
+        }
+        if (io.carry_body_frame && warp == 1) {                            // robot.py:222-229 (D7)
+          const float* r = in.root[lane];
+          float o[3];
+          rotate_inverse(r + 3, r[7], r[8], r[9], o);
+          io.base_lin_vel[ge * 3 + 0] = o[0]; io.base_lin_vel[ge * 3 + 1] = o[1]; io.base_lin_vel[ge * 3 + 2] = o[2];
+          rotate_inverse(r + 3, r[10], r[11], r[12], o);
+          io.base_ang_vel[ge * 3 + 0] = o[0]; io.base_ang_vel[ge * 3 + 1] = o[1]; io.base_ang_vel[ge * 3 + 2] = o[2];
+          rotate_inverse(r + 3, 0.0f, 0.0f, -1.0f, o);
+          io.projected_gravity[ge * 3 + 0] = o[0]; io.projected_gravity[ge * 3 + 1] = o[1];
+          io.projected_gravity[ge * 3 + 2] = o[2];
+        }
+      }
+      pipe::fence_proxy_async();                              // smem writes -> visible to the TMA store
+      pipe::named_barrier(1, V3_B_THREADS);
+      if (t == 0) pipe::mbar_arrive(&s.b_done[b]);
+    }
+    return;
+  }
+
+  // ---------------- C group: thread = scan point ----------------
+  {
+    const int p = t - V3_B_THREADS;                          // 0..191, points 187..191 idle
+    const float bx = k.px[p % A1_NX], by = k.py[(p / A1_NX) % A1_NY];
+    const float hclip = fminf(k.h_clip, k.clip_obs);         // clip(clip(v,+-a),+-b) == clip(v,+-min(a,b))
+    const unsigned max_px = (unsigned)(k.trows - 1), max_py = (unsigned)(k.tcols - 1);
+    const unsigned tiles_y = (unsigned)k.tiles_y, tcols = (unsigned)k.tcols;
+    const short* __restrict__ table = k.table;
+    const f2_t BX = pk(bx, bx), BY = pk(by, by), NBY = pk(-by, -by), BORDER = pk(k.border, k.border);
+    const f2_t RCP = pk(k.hdiv.r, k.hdiv.r), NEGD = pk(-k.hdiv.d, -k.hdiv.d), VS = pk(k.vscale, k.vscale);
+    const f2_t NZ = pk(k.neg_zero, k.neg_zero);
+    for (int j = 0; j < my_tiles; ++j) {
+      const int b = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      const long long e0 = (long long)(first + j * stride) * A1_TILE;
+      pipe::mbar_wait(&s.b_done[b], par);
+      if (p < A1_POINTS) {
+        float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
+        // 8 envs (4 pairs) per batch: all index arithmetic first (packed fp32x2, two envs per
+        // instruction), then the 8 table gathers back to back, then the 8 results.
+#pragma unroll 1
+        for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
+          int idx[8];
+          f2_t ZB[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 a = s.sA[b][q0 + u], bq = s.sB[b][q0 + u], cq = s.sC[b][q0 + u];
+            const f2_t Z2 = pk(a.x, a.y), Z = pk(a.z, a.w), W = pk(bq.x, bq.y), X = pk(bq.z, bq.w);
+            const f2_t Y = pk(cq.x, cq.y);
+            ZB[u] = pk(cq.z, cq.w);
+            // quat_apply_yaw (shifu/utils/terrain.py:202-206) on (bx, by, 0):
+            //   t = 2(q x b) = (-2z*by, 2z*bx);  out = (b + w*t) + q x t,  q x t = (-z*ty, z*tx)
+            // Products that feed an add are written fma(a, b, -0): ptxas contracts
+            // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding) even under --fmad=false,
+            // which flips ~0.3 % of the cell indices; fma(a, b, -0) == RN(a*b) exactly and cannot be
+            // contracted again (NZ comes from a kernel parameter, so it is not constant-folded).
+            const f2_t tx = mul2(Z2, NBY), ty = mul2(Z2, BX);
+            const f2_t rx = sub2(add2(BX, fma2(W, tx, NZ)), fma2(Z, ty, NZ));
+            const f2_t ry = add2(add2(BY, fma2(W, ty, NZ)), fma2(Z, tx, NZ));
+            // + base xy, + border, / horizontal_scale (isaac_gym.py:416-421)
+            const f2_t ax = add2(add2(rx, X), BORDER), ay = add2(add2(ry, Y), BORDER);
+            float fx0, fx1, fy0, fy1;
+            if (EXACT_DIV) {
+              float a0, a1, b0, b1;
+              upk(ax, a0, a1); upk(ay, b0, b1);
+              fx0 = div_rn(a0, k.hdiv.d); fx1 = div_rn(a1, k.hdiv.d);
+              fy0 = div_rn(b0, k.hdiv.d); fy1 = div_rn(b1, k.hdiv.d);
+            } else {                         // q0 = x*r; e = fma(-d, q0, x); q = fma(e, r, q0)
+              const f2_t qx = mul2(ax, RCP), qy = mul2(ay, RCP);
+              upk(fma2(fma2(NEGD, qx, ax), RCP, qx), fx0, fx1);
+              upk(fma2(fma2(NEGD, qy, ay), RCP, qy), fy0, fy1);
+            }
+            // .long() + clip (isaac_gym.py:421-425): float->uint truncates and saturates at 0
+            const unsigned px0 = min(__float2uint_rz(fx0), max_px), px1 = min(__float2uint_rz(fx1), max_px);
+            const unsigned py0 = min(__float2uint_rz(fy0), max_py), py1 = min(__float2uint_rz(fy1), max_py);
+            if (TILED) {
+              idx[2 * u] = (int)((((px0 >> TILE_SHIFT) * tiles_y + (py0 >> TILE_SHIFT)) << (2 * TILE_SHIFT)) |
+                                 ((px0 & 7u) << TILE_SHIFT) | (py0 & 7u));
+              idx[2 * u + 1] = (int)((((px1 >> TILE_SHIFT) * tiles_y + (py1 >> TILE_SHIFT)) << (2 * TILE_SHIFT)) |
+                                     ((px1 & 7u) << TILE_SHIFT) | (py1 & 7u));
+            } else {
+              idx[2 * u] = (int)(px0 * tcols + py0);
+              idx[2 * u + 1] = (int)(px1 * tcols + py1);
+            }
+          }
+          short h[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) h[u] = __ldg(table + idx[u]);          // isaac_gym.py:427-431 (folded)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const f2_t hg = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
+            float v0, v1;
+            upk(sub2(ZB[u], hg), v0, v1);                                     // (z - 0.5) - h, a1_conditional.py:132
+            const int e = 2 * (q0 + u);
+            s.out[b][e][A1_HEAD + p] = clampf(v0, -hclip, hclip);
+            s.out[b][e + 1][A1_HEAD + p] = clampf(v1, -hclip, hclip);
+            if (mrow != nullptr) {
+              float g0, g1;
+              upk(hg, g0, g1);
+              __stcs(mrow + (long long)e * A1_POINTS, g0);
+              __stcs(mrow + (long long)(e + 1) * A1_POINTS, g1);
+            }
+          }
+        }
+      }
+      pipe::fence_proxy_async();
+      pipe::named_barrier(2, V3_C_THREADS);
+      if (p == 0) pipe::mbar_arrive(&s.c_done[b]);
+    }
+  }
+}
+
+}  // namespace shifu

@@ -47,6 +47,7 @@ struct A1K {
   int tiles_y;            // tiles per table row
   int tiled;              // 1: 8x8 tiles, 0: row-major (pitch = tcols)
   double* stats;          // SHIFU_NUM_STATS accumulators
+  float neg_zero;         // -0.0f, opaque to ptxas: see mulx2() in a1_fused_tma.cuh
 };
 
 __device__ __forceinline__ float hdivide(float x, const A1K& k) {

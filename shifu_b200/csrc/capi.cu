@@ -10,6 +10,7 @@
 #include "../../include/shifu_b200.h"
 #include "a1_kernels.cuh"
 #include "a1_fused.cuh"
+#include "a1_fused_tma.cuh"
 #include "abb_kernels.cuh"
 #include "common_kernels.cuh"
 
@@ -58,6 +59,8 @@ struct ShifuCtx {
   unsigned epoch = 0;
   int a1_grid = 0;
   int a1_occ = 0;
+  int tma_occ = 0;
+  bool use_tma = true;
 };
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -111,6 +114,7 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   k.xy_span = (float)((double)d.reset_xy_range - (double)(-d.reset_xy_range)); k.xy_low = -d.reset_xy_range;
   k.force_span = (float)((double)d.push_force_max - (double)(-d.push_force_max)); k.force_low = -d.push_force_max;
   for (int i = 0; i < 3; ++i) { k.cmd_span[i] = (float)((double)d.cmd_high[i] - (double)d.cmd_low[i]); k.cmd_low[i] = d.cmd_low[i]; }
+  k.neg_zero = -0.0f;
   k.curriculum = d.curriculum; k.max_level = d.max_terrain_level; k.n_types = d.num_terrain_types;
   k.up_dist = d.level_up_distance; k.down_factor = d.level_down_factor;
   k.n_terms = d.num_reward_terms;
@@ -205,6 +209,22 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
     const int cap = c->sm_count * (occ > 0 ? occ : 1);
     c->a1_grid = tiles < cap ? tiles : cap;
     c->a1_occ = occ;
+    // pipelined TMA variants: opt in to the large dynamic shared-memory footprint
+    const void* tma_variants[4] = {
+        (const void*)a1_post_physics_tma_kernel<true, false>, (const void*)a1_post_physics_tma_kernel<true, true>,
+        (const void*)a1_post_physics_tma_kernel<false, false>, (const void*)a1_post_physics_tma_kernel<false, true>};
+    for (int v = 0; v < 4 && e == cudaSuccess; ++v) {
+      e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
+    int tocc = 0;
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, a1_post_physics_tma_kernel<true, false>, V3_THREADS,
+                                                        sizeof(V3Smem));
+    c->tma_occ = tocc;
+    const char* kern = getenv("SHIFU_A1_KERNEL");
+    c->use_tma = !(kern != nullptr && strcmp(kern, "phased") == 0);
   }
   if (e != cudaSuccess) {
     int rc = fail((int)e, "shifu_ctx_create: %s", cudaGetErrorString(e));
@@ -316,13 +336,54 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
   for (int j = 0; j < c->a1.num_reward_terms; ++j)
     if (io->ep_sums[j] == nullptr) return fail(SHIFU_E_NULL, "ep_sums[%d] is NULL", j);
   REQUIRE_ALIGNED(io->dof_state, 16);
-  const dim3 grid(c->a1_grid), block(A1_THREADS);
   const bool tiled = c->a1k.tiled != 0, exact = c->a1k.exact_div != 0;
-  if (tiled && !exact) a1_post_physics_kernel<true, false><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
-  else if (tiled && exact) a1_post_physics_kernel<true, true><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
-  else if (!tiled && !exact) a1_post_physics_kernel<false, false><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
-  else a1_post_physics_kernel<false, true><<<grid, block, 0, S(stream)>>>(c->a1k, *io);
-  CUDA_TRY(cudaGetLastError());
+  const int n = c->a1.num_envs;
+
+  // Pipelined TMA kernel for the full 32-env tiles when the layout allows bulk copies
+  // (contiguous root rows, 16-byte aligned tensors); the barrier-phased kernel takes the ragged
+  // tail (< 32 envs) or everything when bulk copies are not possible.
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool can_tma = c->use_tma && c->a1k.root_stride == 1 && c->a1k.root_offset == 0 && al16(io->root_state) &&
+                       al16(io->dof_state) && al16(io->contact_state) && al16(io->history) && al16(io->torques) &&
+                       al16(io->actions) && al16(io->obs_buf);
+  const int full_tiles = can_tma ? n / A1_TILE : 0;
+  if (full_tiles > 0) {
+    const int cap = c->sm_count * (c->tma_occ > 0 ? c->tma_occ : 1);
+    const dim3 grid(full_tiles < cap ? full_tiles : cap), block(V3_THREADS);
+    const size_t smem = sizeof(V3Smem);
+    if (tiled && !exact) a1_post_physics_tma_kernel<true, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    else if (tiled && exact) a1_post_physics_tma_kernel<true, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    else if (!tiled && !exact) a1_post_physics_tma_kernel<false, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    else a1_post_physics_tma_kernel<false, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    CUDA_TRY(cudaGetLastError());
+  }
+  const int done = full_tiles * A1_TILE;
+  if (done < n) {
+    A1K k = c->a1k;
+    ShifuA1StepIO t = *io;
+    if (done > 0) {                       // shift every per-env tensor to the first tail env
+      const size_t e = (size_t)done;
+      k.n = n - done;
+      k.env_offset += done;
+      t.root_state += e * 13; t.dof_state += e * (A1_DOF * 2); t.contact_state += e * (A1_BODIES * 3);
+      t.actions += e * A1_DOF; t.torques += e * A1_DOF; t.history += e * (A1_DOF * A1_HIST);
+      t.command += e * 3; t.ep_len += e;
+      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) if (t.ep_sums[j] != nullptr) t.ep_sums[j] += e;
+      t.base_lin_vel += e * 3; t.base_ang_vel += e * 3; t.projected_gravity += e * 3;
+      t.env_origins += e * 3; t.terrain_levels += e; t.terrain_types += e;
+      t.dof_targets += e * A1_DOF; t.rand_force += e * (A1_BODIES * 3);
+      t.obs_buf += e * A1_OBS; t.rew_buf += e; t.reset_buf += e; t.time_out_buf += e; t.contact_term_buf += e;
+      if (t.measured_heights != nullptr) t.measured_heights += e * A1_POINTS;
+    }
+    const int tiles = (k.n + A1_TILE - 1) / A1_TILE;
+    const int cap = c->sm_count * (c->a1_occ > 0 ? c->a1_occ : 1);
+    const dim3 grid(tiles < cap ? tiles : cap), block(A1_THREADS);
+    if (tiled && !exact) a1_post_physics_kernel<true, false><<<grid, block, 0, S(stream)>>>(k, t);
+    else if (tiled && exact) a1_post_physics_kernel<true, true><<<grid, block, 0, S(stream)>>>(k, t);
+    else if (!tiled && !exact) a1_post_physics_kernel<false, false><<<grid, block, 0, S(stream)>>>(k, t);
+    else a1_post_physics_kernel<false, true><<<grid, block, 0, S(stream)>>>(k, t);
+    CUDA_TRY(cudaGetLastError());
+  }
   return SHIFU_OK;
 }
 

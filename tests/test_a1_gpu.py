@@ -73,9 +73,11 @@ def test_golden_a1_fullmap(carry):
     _replay_golden("a1_fullmap", carry)
 
 
-@pytest.mark.parametrize("n", [1, 33, 1000, 4096])
+@pytest.mark.parametrize("n", [1, 33, 1000, 4096, 32 * 1200 + 7])
 def test_oracle_parity_random(n):
-    """Fresh seeded inputs, default 1300x2100 map, ragged sizes; oracle (CPU) vs CUDA."""
+    """Fresh seeded inputs, default 1300x2100 map, ragged sizes; oracle (CPU) vs CUDA.
+    The largest size gives every persistent CTA several tiles (shared-memory buffer reuse in the
+    TMA pipeline) plus a ragged tail handled by the barrier-phased kernel."""
     from oracle import shifu_oracle as so
     from shifu_b200.sim.synthetic import a1_snapshot
     hs, origins, types, env_origins = _terrain(n)
