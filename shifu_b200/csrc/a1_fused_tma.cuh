@@ -45,7 +45,7 @@ struct alignas(128) V3Smem {
   float4 sB[2][A1_TILE / 2];
   float4 sC[2][A1_TILE / 2];
   float rterm[SHIFU_MAX_REWARD_TERMS][A1_TILE];
-  float cla[A1_TILE][9];
+  float cla[2][A1_TILE][9];           // command (post-reset), base lin vel, base ang vel
   uint64_t full_in[2], b_done[2], c_done[2], free_buf[2];
 };
 
@@ -144,11 +144,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const int b = j & 1;
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
-      pipe::mbar_wait(&s.b_done[b], par);                     // history pushed, head written
-      pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
-      pipe::bulk_commit();
-      pipe::mbar_wait(&s.c_done[b], par);                     // heights written
+      pipe::mbar_wait(&s.c_done[b], par);                     // obs tile complete, history pushed
       pipe::bulk_store(io.obs_buf + e0 * A1_OBS, s.out[b], V3_OUT_BYTES);
+      pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
       pipe::bulk_commit();
       pipe::bulk_wait_read_all();                             // smem of this buffer is reusable
       if (j + 2 < my_tiles)
@@ -189,12 +187,15 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       float esum[SHIFU_MAX_REWARD_TERMS];
 #pragma unroll
       for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) esum[q] = es_n[q];
+      float c9[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) c9[q] = c9_n[q];
+      if (warp == 0 && j + 1 < my_tiles) prefetch(j + 1);    // next tile's scalars in flight
+      if (j >= 2) pipe::mbar_wait(&s.free_buf[b], par ^ 1);   // buffers of tile j-2 consumed
       if (warp == 0) {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) s.cla[lane][q] = c9_n[q];
-        if (j + 1 < my_tiles) prefetch(j + 1);
+        for (int q = 0; q < 9; ++q) s.cla[b][lane][q] = c9[q];
       }
-      if (j >= 2) pipe::mbar_wait(&s.free_buf[b], par ^ 1);   // out/ev/pos of tile j-2 consumed
       pipe::mbar_wait(&s.full_in[b], par);                    // tile rows have landed
       pipe::named_barrier(1, V3_B_THREADS);                   // cla visible to both warps
 
@@ -202,7 +203,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       bool contact_term = false;
 #pragma unroll 1
       for (int q = warp; q < k.n_terms; q += 2)
-        s.rterm[q][lane] = v3_eval_term(k.terms[q], k.rp[q][0], k.rp[q][1], k, in, s.cla[lane], lane);
+        s.rterm[q][lane] = v3_eval_term(k.terms[q], k.rp[q][0], k.rp[q][1], k, in, s.cla[b][lane], lane);
       if (warp == 0) {                                                    // a1_conditional.py:146-148
         const float* fb = &in.contact[lane][k.base_body * 3];
         contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
@@ -242,10 +243,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         io.time_out_buf[ge] = time_out ? 1 : 0;
         io.contact_term_buf[ge] = contact_term ? 1 : 0;
         if (reset) {                                                       // env.py:101-102
-          float cmd[3] = {s.cla[lane][0], s.cla[lane][1], s.cla[lane][2]};
+          float cmd[3] = {s.cla[b][lane][0], s.cla[b][lane][1], s.cla[b][lane][2]};
           a1_reset_env<true>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
                              st_sum, level_delta);
-          s.cla[lane][0] = cmd[0]; s.cla[lane][1] = cmd[1]; s.cla[lane][2] = cmd[2];
+          s.cla[b][lane][0] = cmd[0]; s.cla[b][lane][1] = cmd[1]; s.cla[b][lane][2] = cmd[2];
         }
         io.ep_len[ge] = len;
 #pragma unroll
@@ -255,43 +256,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             sub_rn(in.root[lane][2], k.h_off);                              // post-reset base z (D8)
         a1_log_sums(k, reset, st_sum, level_delta, lane);
       }
-      pipe::named_barrier(1, V3_B_THREADS);
-
-      // ---- B3: obs head (a1_conditional.py:131-144), history push (train.py:12-14), carry
-      {
-        const float c = k.clip_obs;
-        for (int i = t; i < A1_TILE * A1_DOF; i += V3_B_THREADS) {
-          const int e = i / A1_DOF, d = i - e * A1_DOF;
-          float* h = s.out[b][e];
-          h[12 + d] = clampf(sub_rn(in.dof[e][2 * d], k.q0[d]), -c, c);
-          h[24 + d] = clampf(in.dof[e][2 * d + 1], -c, c);
-          const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
-                      a2 = in.hist[e][d * A1_HIST + 2];
-          h[36 + d] = clampf(a0, -c, c);               // HistoryRecorder.flatten: slot-major
-          h[48 + d] = clampf(a1, -c, c);
-          h[60 + d] = clampf(a2, -c, c);
-          in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
-          in.hist[e][d * A1_HIST + 1] = a0;
-          in.hist[e][d * A1_HIST + 0] = in.act[e][d];
-        }
-        for (int i = t; i < A1_TILE * 12; i += V3_B_THREADS) {
-          const int e = i / 12, q = i - e * 12;
-          const float v = (q < 9) ? s.cla[e][q] : ((q == 11) ? -1.0f : 0.0f);
-          s.out[b][e][q] = clampf(v, -c, c);
-        }
-        if (io.carry_body_frame && warp == 1) {                            // robot.py:222-229 (D7)
-          const float* r = in.root[lane];
-          float o[3];
-          rotate_inverse(r + 3, r[7], r[8], r[9], o);
-          io.base_lin_vel[ge * 3 + 0] = o[0]; io.base_lin_vel[ge * 3 + 1] = o[1]; io.base_lin_vel[ge * 3 + 2] = o[2];
-          rotate_inverse(r + 3, r[10], r[11], r[12], o);
-          io.base_ang_vel[ge * 3 + 0] = o[0]; io.base_ang_vel[ge * 3 + 1] = o[1]; io.base_ang_vel[ge * 3 + 2] = o[2];
-          rotate_inverse(r + 3, 0.0f, 0.0f, -1.0f, o);
-          io.projected_gravity[ge * 3 + 0] = o[0]; io.projected_gravity[ge * 3 + 1] = o[1];
-          io.projected_gravity[ge * 3 + 2] = o[2];
-        }
-      }
-      pipe::fence_proxy_async();                              // smem writes -> visible to the TMA store
+      // post-reset rows / command / zb are final: hand the tile to the C group
       pipe::named_barrier(1, V3_B_THREADS);
       if (t == 0) pipe::mbar_arrive(&s.b_done[b]);
     }
@@ -314,8 +279,47 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       pipe::mbar_wait(&s.b_done[b], par);
+      // ---- obs head (a1_conditional.py:131-144) + history push (train.py:12-14): post-reset rows
+      {
+        V3In& in = s.in[b];
+        const float c = k.clip_obs;
+        for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
+          const int e = i / A1_DOF, d = i - e * A1_DOF;
+          float* h = s.out[b][e];
+          const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
+          h[12 + d] = clampf(sub_rn(qd.x, k.q0[d]), -c, c);
+          h[24 + d] = clampf(qd.y, -c, c);
+          const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
+                      a2 = in.hist[e][d * A1_HIST + 2];
+          h[36 + d] = clampf(a0, -c, c);               // HistoryRecorder.flatten: slot-major
+          h[48 + d] = clampf(a1, -c, c);
+          h[60 + d] = clampf(a2, -c, c);
+          in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
+          in.hist[e][d * A1_HIST + 1] = a0;
+          in.hist[e][d * A1_HIST + 0] = in.act[e][d];
+        }
+        for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
+          const int e = i / 12, q = i - e * 12;
+          const float v = (q < 9) ? s.cla[b][e][q] : ((q == 11) ? -1.0f : 0.0f);
+          s.out[b][e][q] = clampf(v, -c, c);
+        }
+        // carried body-frame velocities for the next control step (robot.py:222-229, D7)
+        if (io.carry_body_frame && p >= V3_C_THREADS - 32) {
+          const int e = p - (V3_C_THREADS - 32);
+          const long long ge = e0 + e;
+          const float* r = in.root[e];
+          float o[3];
+          rotate_inverse(r + 3, r[7], r[8], r[9], o);
+          io.base_lin_vel[ge * 3 + 0] = o[0]; io.base_lin_vel[ge * 3 + 1] = o[1]; io.base_lin_vel[ge * 3 + 2] = o[2];
+          rotate_inverse(r + 3, r[10], r[11], r[12], o);
+          io.base_ang_vel[ge * 3 + 0] = o[0]; io.base_ang_vel[ge * 3 + 1] = o[1]; io.base_ang_vel[ge * 3 + 2] = o[2];
+          rotate_inverse(r + 3, 0.0f, 0.0f, -1.0f, o);
+          io.projected_gravity[ge * 3 + 0] = o[0]; io.projected_gravity[ge * 3 + 1] = o[1];
+          io.projected_gravity[ge * 3 + 2] = o[2];
+        }
+      }
       if (p < A1_POINTS) {
-        float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
+        float* mrow =(io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
         // 8 envs (4 pairs) per batch: all index arithmetic first (packed fp32x2, two envs per
         // instruction), then the 8 table gathers back to back, then the 8 results.
 #pragma unroll 1
