@@ -21,8 +21,9 @@
 
 namespace shifu {
 
-constexpr int V3_B_THREADS = 64, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
-constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;   // 288
+// two B groups of 2 warps each: group g owns the tiles (and shared-memory buffers) of parity g
+constexpr int V3_BG_THREADS = 64, V3_B_THREADS = 2 * V3_BG_THREADS, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
+constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;   // 352
 
 struct alignas(128) V3In {            // one tile of simulator/env rows, each member 16-B aligned
   float root[A1_TILE][13];            //  1664 B
@@ -41,12 +42,13 @@ struct alignas(128) V3Smem {
   // two packed fp32x2 operands: sA = (2zq_e, 2zq_e1, zq_e, zq_e1), sB = (wq_e, wq_e1, x_e, x_e1),
   // sC = (y_e, y_e1, zb_e, zb_e1); (zq, wq) = normalised yaw quaternion of the PRE-reset pose,
   // zb = z_postreset - 0.5
-  float4 sA[2][A1_TILE / 2];
-  float4 sB[2][A1_TILE / 2];
-  float4 sC[2][A1_TILE / 2];
-  float rterm[SHIFU_MAX_REWARD_TERMS][A1_TILE];
-  float cla[2][A1_TILE][9];           // command (post-reset), base lin vel, base ang vel
-  uint64_t full_in[2], b_done[2], c_done[2], free_buf[2];
+  // (4-deep ring: the B groups may run ahead of the scan group without an extra hand-shake)
+  float4 sA[4][A1_TILE / 2];
+  float4 sB[4][A1_TILE / 2];
+  float4 sC[4][A1_TILE / 2];
+  float rterm[2][SHIFU_MAX_REWARD_TERMS][A1_TILE];
+  float cla[4][A1_TILE][9];           // command (post-reset), base lin vel, base ang vel
+  uint64_t full_in[2], b_done[2], h_done[2], c_done[2], free_buf[2];
 };
 
 constexpr uint32_t V3_IN_BYTES = sizeof(V3In);
@@ -127,6 +129,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       pipe::mbar_init(&s.full_in[b], 1);
       pipe::mbar_init(&s.b_done[b], 1);
+      pipe::mbar_init(&s.h_done[b], 1);
       pipe::mbar_init(&s.c_done[b], 1);
       pipe::mbar_init(&s.free_buf[b], 1);
     }
@@ -144,13 +147,18 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const int b = j & 1;
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
-      pipe::mbar_wait(&s.c_done[b], par);                     // obs tile complete, history pushed
-      pipe::bulk_store(io.obs_buf + e0 * A1_OBS, s.out[b], V3_OUT_BYTES);
+      // input rows are dead once the head / history phase is over: store the pushed history and
+      // refill the stage right away, long before the tile's height scan finishes
+      pipe::mbar_wait<128>(&s.h_done[b], par);
       pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
       pipe::bulk_commit();
-      pipe::bulk_wait_read_all();                             // smem of this buffer is reusable
+      pipe::bulk_wait_read_all();
       if (j + 2 < my_tiles)
         v3_issue_loads(s.in[b], io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
+      pipe::mbar_wait<256>(&s.c_done[b], par);                // obs tile complete
+      pipe::bulk_store(io.obs_buf + e0 * A1_OBS, s.out[b], V3_OUT_BYTES);
+      pipe::bulk_commit();
+      pipe::bulk_wait_read_all();                             // obs tile buffer reusable
       pipe::mbar_arrive(&s.free_buf[b]);
     }
     pipe::bulk_wait_all();                                    // global writes done before exit
@@ -158,8 +166,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
   }
 
   if (t < V3_B_THREADS) {
-    // ---------------- B group: lane = env ----------------
-    const int warp = t >> 5, lane = t & 31;
+    // ---------------- B groups: lane = env ----------------
+    const int g = t / V3_BG_THREADS, tg = t % V3_BG_THREADS;   // group g handles tiles j = g, g+2, ...
+    const int warp = tg >> 5, lane = tg & 31;
     long long len_n = 0;
     float c9_n[9], es_n[SHIFU_MAX_REWARD_TERMS];
     // software-pipelined per-env scalars (warp 0 only): loaded one tile ahead
@@ -175,10 +184,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
       for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) es_n[q] = (q < k.n_terms) ? io.ep_sums[q][ge] : 0.0f;
     };
-    if (warp == 0 && my_tiles > 0) prefetch(0);
+    if (warp == 0 && g < my_tiles) prefetch(g);
 
-    for (int j = 0; j < my_tiles; ++j) {
-      const int b = j & 1;
+    for (int j = g; j < my_tiles; j += 2) {
+      const int b = j & 1;                                    // == g
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       const long long ge = e0 + lane;
@@ -190,20 +199,20 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       float c9[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) c9[q] = c9_n[q];
-      if (warp == 0 && j + 1 < my_tiles) prefetch(j + 1);    // next tile's scalars in flight
-      if (j >= 2) pipe::mbar_wait(&s.free_buf[b], par ^ 1);   // buffers of tile j-2 consumed
+      if (warp == 0 && j + 2 < my_tiles) prefetch(j + 2);    // this group's next tile: scalars in flight
+      const int rb = j & 3;                                   // scalar ring stage (see V3Smem)
       if (warp == 0) {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) s.cla[b][lane][q] = c9[q];
+        for (int q = 0; q < 9; ++q) s.cla[rb][lane][q] = c9[q];
       }
       pipe::mbar_wait(&s.full_in[b], par);                    // tile rows have landed
-      pipe::named_barrier(1, V3_B_THREADS);                   // cla visible to both warps
+      pipe::named_barrier(1 + g, V3_BG_THREADS);              // cla visible to both warps
 
       // ---- B1: reward terms (warp w takes terms w, w+2, ...), termination, yaw normalisation
       bool contact_term = false;
 #pragma unroll 1
       for (int q = warp; q < k.n_terms; q += 2)
-        s.rterm[q][lane] = v3_eval_term(k.terms[q], k.rp[q][0], k.rp[q][1], k, in, s.cla[b][lane], lane);
+        s.rterm[g][q][lane] = v3_eval_term(k.terms[q], k.rp[q][0], k.rp[q][1], k, in, s.cla[rb][lane], lane);
       if (warp == 0) {                                                    // a1_conditional.py:146-148
         const float* fb = &in.contact[lane][k.base_body * 3];
         contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
@@ -211,14 +220,14 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         // heights are measured at the PRE-reset pose (isaac_gym.py:320-322 runs before post_step)
         const ScanEnv ev = make_scan_env(in.root[lane]);
         const int q = lane >> 1, sl = lane & 1;
-        float* a = reinterpret_cast<float*>(&s.sA[b][q]);
-        float* bb = reinterpret_cast<float*>(&s.sB[b][q]);
-        float* cc = reinterpret_cast<float*>(&s.sC[b][q]);
+        float* a = reinterpret_cast<float*>(&s.sA[rb][q]);
+        float* bb = reinterpret_cast<float*>(&s.sB[rb][q]);
+        float* cc = reinterpret_cast<float*>(&s.sC[rb][q]);
         a[sl] = ev.z2; a[2 + sl] = ev.z;
         bb[sl] = ev.w; bb[2 + sl] = ev.x;
         cc[sl] = ev.y;
       }
-      pipe::named_barrier(1, V3_B_THREADS);
+      pipe::named_barrier(1 + g, V3_BG_THREADS);
 
       // ---- B2: warp 0 — ordered accumulation, flags, reset, log sums
       if (warp == 0) {
@@ -233,7 +242,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) {
           if (q < k.n_terms) {
-            const float r = s.rterm[q][lane];
+            const float r = s.rterm[g][q][lane];
             esum[q] = add_rn(esum[q], r);
             rew = add_rn(rew, r);
           }
@@ -243,22 +252,22 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         io.time_out_buf[ge] = time_out ? 1 : 0;
         io.contact_term_buf[ge] = contact_term ? 1 : 0;
         if (reset) {                                                       // env.py:101-102
-          float cmd[3] = {s.cla[b][lane][0], s.cla[b][lane][1], s.cla[b][lane][2]};
+          float cmd[3] = {s.cla[rb][lane][0], s.cla[rb][lane][1], s.cla[rb][lane][2]};
           a1_reset_env<true>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
                              st_sum, level_delta);
-          s.cla[b][lane][0] = cmd[0]; s.cla[b][lane][1] = cmd[1]; s.cla[b][lane][2] = cmd[2];
+          s.cla[rb][lane][0] = cmd[0]; s.cla[rb][lane][1] = cmd[1]; s.cla[rb][lane][2] = cmd[2];
         }
         io.ep_len[ge] = len;
 #pragma unroll
         for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q)
           if (q < k.n_terms) io.ep_sums[q][ge] = esum[q];
-        reinterpret_cast<float*>(&s.sC[b][lane >> 1])[2 + (lane & 1)] =
+        reinterpret_cast<float*>(&s.sC[rb][lane >> 1])[2 + (lane & 1)] =
             sub_rn(in.root[lane][2], k.h_off);                              // post-reset base z (D8)
         a1_log_sums(k, reset, st_sum, level_delta, lane);
       }
       // post-reset rows / command / zb are final: hand the tile to the C group
-      pipe::named_barrier(1, V3_B_THREADS);
-      if (t == 0) pipe::mbar_arrive(&s.b_done[b]);
+      pipe::named_barrier(1 + g, V3_BG_THREADS);
+      if (tg == 0) pipe::mbar_arrive(&s.b_done[b]);
     }
     return;
   }
@@ -278,7 +287,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const int b = j & 1;
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
+      const int rb = j & 3;
       pipe::mbar_wait(&s.b_done[b], par);
+      if (j >= 2) pipe::mbar_wait(&s.free_buf[b], par ^ 1);   // obs tile of j-2 has left shared memory
       // ---- obs head (a1_conditional.py:131-144) + history push (train.py:12-14): post-reset rows
       {
         V3In& in = s.in[b];
@@ -300,7 +311,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         }
         for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
           const int e = i / 12, q = i - e * 12;
-          const float v = (q < 9) ? s.cla[b][e][q] : ((q == 11) ? -1.0f : 0.0f);
+          const float v = (q < 9) ? s.cla[rb][e][q] : ((q == 11) ? -1.0f : 0.0f);
           s.out[b][e][q] = clampf(v, -c, c);
         }
         // carried body-frame velocities for the next control step (robot.py:222-229, D7)
@@ -318,6 +329,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           io.projected_gravity[ge * 3 + 2] = o[2];
         }
       }
+      pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
+      pipe::named_barrier(3, V3_C_THREADS);
+      if (p == 0) pipe::mbar_arrive(&s.h_done[b]);
       if (p < A1_POINTS) {
         float* mrow =(io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
         // 8 envs (4 pairs) per batch: all index arithmetic first (packed fp32x2, two envs per
@@ -328,7 +342,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           f2_t ZB[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float4 a = s.sA[b][q0 + u], bq = s.sB[b][q0 + u], cq = s.sC[b][q0 + u];
+            const float4 a = s.sA[rb][q0 + u], bq = s.sB[rb][q0 + u], cq = s.sC[rb][q0 + u];
             const f2_t Z2 = pk(a.x, a.y), Z = pk(a.z, a.w), W = pk(bq.x, bq.y), X = pk(bq.z, bq.w);
             const f2_t Y = pk(cq.x, cq.y);
             ZB[u] = pk(cq.z, cq.w);
@@ -388,7 +402,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         }
       }
       pipe::fence_proxy_async();
-      pipe::named_barrier(2, V3_C_THREADS);
+      pipe::named_barrier(3, V3_C_THREADS);
       if (p == 0) pipe::mbar_arrive(&s.c_done[b]);
     }
   }

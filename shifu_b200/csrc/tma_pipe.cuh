@@ -37,6 +37,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 
 // Wait for the phase with the given parity to complete.  try_wait sleeps in hardware; the spin
 // bound turns a protocol bug into a trap instead of a hung GPU.
+template <unsigned SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -49,7 +50,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (!done) {
-      __nanosleep(32);                 // do not burn issue slots of the working warps while polling
+      __nanosleep(SLEEP_NS);           // do not burn issue slots of the working warps while polling
       if (spin > (1u << 24)) __trap();
     }
   }
