@@ -128,9 +128,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       pipe::mbar_init(&s.full_in[b], 1);
-      pipe::mbar_init(&s.b_done[b], 1);
-      pipe::mbar_init(&s.h_done[b], 1);
-      pipe::mbar_init(&s.c_done[b], 1);
+      // every thread of the producing group arrives itself: no group barrier, fast warps move on
+      pipe::mbar_init(&s.b_done[b], V3_BG_THREADS);
+      pipe::mbar_init(&s.h_done[b], V3_C_THREADS);
+      pipe::mbar_init(&s.c_done[b], V3_C_THREADS);
       pipe::mbar_init(&s.free_buf[b], 1);
     }
     pipe::fence_barrier_init();
@@ -155,7 +156,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       pipe::bulk_wait_read_all();
       if (j + 2 < my_tiles)
         v3_issue_loads(s.in[b], io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
-      pipe::mbar_wait<256>(&s.c_done[b], par);                // obs tile complete
+      pipe::mbar_wait<512>(&s.c_done[b], par);                // obs tile complete
       pipe::bulk_store(io.obs_buf + e0 * A1_OBS, s.out[b], V3_OUT_BYTES);
       pipe::bulk_commit();
       pipe::bulk_wait_read_all();                             // obs tile buffer reusable
@@ -205,7 +206,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 9; ++q) s.cla[rb][lane][q] = c9[q];
       }
-      pipe::mbar_wait(&s.full_in[b], par);                    // tile rows have landed
+      pipe::mbar_wait<256>(&s.full_in[b], par);               // tile rows have landed
       pipe::named_barrier(1 + g, V3_BG_THREADS);              // cla visible to both warps
 
       // ---- B1: reward terms (warp w takes terms w, w+2, ...), termination, yaw normalisation
@@ -266,8 +267,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         a1_log_sums(k, reset, st_sum, level_delta, lane);
       }
       // post-reset rows / command / zb are final: hand the tile to the C group
-      pipe::named_barrier(1 + g, V3_BG_THREADS);
-      if (tg == 0) pipe::mbar_arrive(&s.b_done[b]);
+      pipe::mbar_arrive(&s.b_done[b]);
     }
     return;
   }
@@ -330,8 +330,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         }
       }
       pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
-      pipe::named_barrier(3, V3_C_THREADS);
-      if (p == 0) pipe::mbar_arrive(&s.h_done[b]);
+      pipe::mbar_arrive(&s.h_done[b]);
       if (p < A1_POINTS) {
         float* mrow =(io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
         // 8 envs (4 pairs) per batch: all index arithmetic first (packed fp32x2, two envs per
@@ -402,8 +401,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         }
       }
       pipe::fence_proxy_async();
-      pipe::named_barrier(3, V3_C_THREADS);
-      if (p == 0) pipe::mbar_arrive(&s.c_done[b]);
+      pipe::mbar_arrive(&s.c_done[b]);
     }
   }
 }
