@@ -22,7 +22,9 @@
 namespace shifu {
 
 // two B groups of 2 warps each: group g owns the tiles (and shared-memory buffers) of parity g
-constexpr int V3_BG_THREADS = 64, V3_B_THREADS = 2 * V3_BG_THREADS, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
+constexpr int V3_B_GROUPS = 1;   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
+constexpr int V3_CTAS_PER_SM = 3;
+constexpr int V3_BG_THREADS = 64, V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
 constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;   // 352
 
 struct alignas(128) V3In {            // one tile of simulator/env rows, each member 16-B aligned
@@ -37,7 +39,6 @@ static_assert(sizeof(V3In) == 18944, "tile layout");
 
 struct alignas(128) V3Smem {
   V3In in[2];
-  float out[2][A1_TILE][A1_OBS];      // obs tiles, 33152 B each
   // per-env scan scalars, laid out per env PAIR (e, e+1) so that one 128-bit broadcast load yields
   // two packed fp32x2 operands: sA = (2zq_e, 2zq_e1, zq_e, zq_e1), sB = (wq_e, wq_e1, x_e, x_e1),
   // sC = (y_e, y_e1, zb_e, zb_e1); (zq, wq) = normalised yaw quaternion of the PRE-reset pose,
@@ -48,11 +49,10 @@ struct alignas(128) V3Smem {
   float4 sC[4][A1_TILE / 2];
   float rterm[2][SHIFU_MAX_REWARD_TERMS][A1_TILE];
   float cla[4][A1_TILE][9];           // command (post-reset), base lin vel, base ang vel
-  uint64_t full_in[2], b_done[2], h_done[2], c_done[2], free_buf[2];
+  uint64_t full_in[2], b_done[2], h_done[2];
 };
 
 constexpr uint32_t V3_IN_BYTES = sizeof(V3In);
-constexpr uint32_t V3_OUT_BYTES = A1_TILE * A1_OBS * 4;
 constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
 
 __device__ __forceinline__ void v3_issue_loads(V3In& in, const ShifuA1StepIO& io, long long e0, uint64_t* bar) {
@@ -115,7 +115,7 @@ __device__ __noinline__ float v3_eval_term(int code, float p0, float p1, const A
 // Processes tiles [0, num_tiles) of 32 envs each (the ragged tail, if any, is a separate launch of
 // the barrier-phased kernel).  Requires root_stride == 1 and 16-byte aligned tensors.
 template <bool TILED, bool EXACT_DIV>
-__global__ void __launch_bounds__(V3_THREADS, 2)
+__global__ void __launch_bounds__(V3_THREADS, V3_CTAS_PER_SM)
 a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V3Smem& s = *reinterpret_cast<V3Smem*>(smem_raw);
@@ -131,8 +131,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       // every thread of the producing group arrives itself: no group barrier, fast warps move on
       pipe::mbar_init(&s.b_done[b], V3_BG_THREADS);
       pipe::mbar_init(&s.h_done[b], V3_C_THREADS);
-      pipe::mbar_init(&s.c_done[b], V3_C_THREADS);
-      pipe::mbar_init(&s.free_buf[b], 1);
     }
     pipe::fence_barrier_init();
   }
@@ -156,11 +154,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       pipe::bulk_wait_read_all();
       if (j + 2 < my_tiles)
         v3_issue_loads(s.in[b], io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
-      pipe::mbar_wait<512>(&s.c_done[b], par);                // obs tile complete
-      pipe::bulk_store(io.obs_buf + e0 * A1_OBS, s.out[b], V3_OUT_BYTES);
-      pipe::bulk_commit();
-      pipe::bulk_wait_read_all();                             // obs tile buffer reusable
-      pipe::mbar_arrive(&s.free_buf[b]);
     }
     pipe::bulk_wait_all();                                    // global writes done before exit
     return;
@@ -187,7 +180,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     };
     if (warp == 0 && g < my_tiles) prefetch(g);
 
-    for (int j = g; j < my_tiles; j += 2) {
+    for (int j = g; j < my_tiles; j += V3_B_GROUPS) {
       const int b = j & 1;                                    // == g
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
@@ -200,7 +193,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       float c9[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) c9[q] = c9_n[q];
-      if (warp == 0 && j + 2 < my_tiles) prefetch(j + 2);    // this group's next tile: scalars in flight
+      if (warp == 0 && j + V3_B_GROUPS < my_tiles) prefetch(j + V3_B_GROUPS);    // this group's next tile: scalars in flight
       const int rb = j & 3;                                   // scalar ring stage (see V3Smem)
       if (warp == 0) {
 #pragma unroll
@@ -289,22 +282,21 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       const int rb = j & 3;
       pipe::mbar_wait(&s.b_done[b], par);
-      if (j >= 2) pipe::mbar_wait(&s.free_buf[b], par ^ 1);   // obs tile of j-2 has left shared memory
       // ---- obs head (a1_conditional.py:131-144) + history push (train.py:12-14): post-reset rows
       {
         V3In& in = s.in[b];
         const float c = k.clip_obs;
         for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
           const int e = i / A1_DOF, d = i - e * A1_DOF;
-          float* h = s.out[b][e];
+          float* h = io.obs_buf + (e0 + e) * A1_OBS;
           const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
-          h[12 + d] = clampf(sub_rn(qd.x, k.q0[d]), -c, c);
-          h[24 + d] = clampf(qd.y, -c, c);
+          __stcs(h + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
+          __stcs(h + 24 + d, clampf(qd.y, -c, c));
           const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
                       a2 = in.hist[e][d * A1_HIST + 2];
-          h[36 + d] = clampf(a0, -c, c);               // HistoryRecorder.flatten: slot-major
-          h[48 + d] = clampf(a1, -c, c);
-          h[60 + d] = clampf(a2, -c, c);
+          __stcs(h + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
+          __stcs(h + 48 + d, clampf(a1, -c, c));
+          __stcs(h + 60 + d, clampf(a2, -c, c));
           in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
           in.hist[e][d * A1_HIST + 1] = a0;
           in.hist[e][d * A1_HIST + 0] = in.act[e][d];
@@ -312,7 +304,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
           const int e = i / 12, q = i - e * 12;
           const float v = (q < 9) ? s.cla[rb][e][q] : ((q == 11) ? -1.0f : 0.0f);
-          s.out[b][e][q] = clampf(v, -c, c);
+          __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
         }
         // carried body-frame velocities for the next control step (robot.py:222-229, D7)
         if (io.carry_body_frame && p >= V3_C_THREADS - 32) {
@@ -332,7 +324,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
       pipe::mbar_arrive(&s.h_done[b]);
       if (p < A1_POINTS) {
-        float* mrow =(io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
+        float* orow = io.obs_buf + e0 * A1_OBS + A1_HEAD + p;
+        float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
         // 8 envs (4 pairs) per batch: all index arithmetic first (packed fp32x2, two envs per
         // instruction), then the 8 table gathers back to back, then the 8 results.
 #pragma unroll 1
@@ -389,8 +382,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             float v0, v1;
             upk(sub2(ZB[u], hg), v0, v1);                                     // (z - 0.5) - h, a1_conditional.py:132
             const int e = 2 * (q0 + u);
-            s.out[b][e][A1_HEAD + p] = clampf(v0, -hclip, hclip);
-            s.out[b][e + 1][A1_HEAD + p] = clampf(v1, -hclip, hclip);
+            __stcs(orow + (long long)e * A1_OBS, clampf(v0, -hclip, hclip));
+            __stcs(orow + (long long)(e + 1) * A1_OBS, clampf(v1, -hclip, hclip));
             if (mrow != nullptr) {
               float g0, g1;
               upk(hg, g0, g1);
@@ -400,8 +393,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           }
         }
       }
-      pipe::fence_proxy_async();
-      pipe::mbar_arrive(&s.c_done[b]);
     }
   }
 }
