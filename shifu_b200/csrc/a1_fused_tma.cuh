@@ -22,8 +22,14 @@
 namespace shifu {
 
 // two B groups of 2 warps each: group g owns the tiles (and shared-memory buffers) of parity g
-constexpr int V3_B_GROUPS = 1;   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
-constexpr int V3_CTAS_PER_SM = 3;
+#ifndef V3_B_GROUPS_CFG
+#define V3_B_GROUPS_CFG 2
+#endif
+#ifndef V3_CTAS_CFG
+#define V3_CTAS_CFG 3
+#endif
+constexpr int V3_B_GROUPS = V3_B_GROUPS_CFG;   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
+constexpr int V3_CTAS_PER_SM = V3_CTAS_CFG;
 constexpr int V3_BG_THREADS = 64, V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
 constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;   // 352
 
@@ -47,7 +53,7 @@ struct alignas(128) V3Smem {
   float4 sA[4][A1_TILE / 2];
   float4 sB[4][A1_TILE / 2];
   float4 sC[4][A1_TILE / 2];
-  float rterm[2][SHIFU_MAX_REWARD_TERMS][A1_TILE];
+  float rterm[V3_B_GROUPS][SHIFU_MAX_REWARD_TERMS][A1_TILE];
   float cla[4][A1_TILE][9];           // command (post-reset), base lin vel, base ang vel
   uint64_t full_in[2], b_done[2], h_done[2];
 };
