@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -212,15 +212,37 @@ def time_e2e(hp, raw_actions, steps, warmup):
     h2d = sum(t.numel() * t.element_size() for t in (h_root, h_dof, h_contact, h_act))
     d2h = sum(t.numel() * t.element_size() for t in (h_obs, h_rew, h_reset))
 
+    # Three streams so that the upload of step t+1 (host->device) overlaps the read-back of step t
+    # (device->host) — PCIe is full duplex; events keep every buffer single-owner:
+    #   in:      wait compute(t-1) done -> H2D state/actions of step t
+    #   compute: wait in(t), wait out(t-1) done -> the step
+    #   out:     wait compute(t) -> D2H obs / rew / reset
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in, ev_cmp, ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    for s in (s_in, s_cmp, s_out):
+        s.wait_stream(torch.cuda.current_stream())
+    ev_cmp.record(s_cmp)
+    ev_out.record(s_out)
+
     def one():
-        hp.root_state.copy_(h_root, non_blocking=True)
-        hp.dof_state.copy_(h_dof, non_blocking=True)
-        hp.contact_state.copy_(h_contact, non_blocking=True)
-        d_act.copy_(h_act, non_blocking=True)
-        hp.step_resident(d_act)
-        h_obs.copy_(hp.obs_buf, non_blocking=True)
-        h_rew.copy_(hp.rew_buf, non_blocking=True)
-        h_reset.copy_(hp.reset_buf, non_blocking=True)
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_cmp)
+            hp.root_state.copy_(h_root, non_blocking=True)
+            hp.dof_state.copy_(h_dof, non_blocking=True)
+            hp.contact_state.copy_(h_contact, non_blocking=True)
+            d_act.copy_(h_act, non_blocking=True)
+            ev_in.record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in)
+            s_cmp.wait_event(ev_out)
+            hp.step_resident(d_act)
+            ev_cmp.record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp)
+            h_obs.copy_(hp.obs_buf, non_blocking=True)
+            h_rew.copy_(hp.rew_buf, non_blocking=True)
+            h_reset.copy_(hp.reset_buf, non_blocking=True)
+            ev_out.record(s_out)
 
     for _ in range(warmup):
         one()
@@ -230,6 +252,7 @@ def time_e2e(hp, raw_actions, steps, warmup):
         one()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    torch.cuda.current_stream().wait_stream(s_cmp)
     return dt * 1e3, h2d, d2h, float(h_rew.mean())
 
 
@@ -284,7 +307,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -344,7 +367,7 @@ def run_ours(args):
                              % ((B_ALG_POST + 4 * B_ALG_PD) * n / 1e6),
                        "reset_fraction_per_step": reset_frac, "launch": "direct (8 launches/step)",
                        "collective": "all_reduce(16 x f64) per step" if world > 1 else "none"},
-            "roofline": {"bound": "hbm", "kernel": "a1_post_physics_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "a1_post_physics_tma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_env": B_ALG_POST,
                          "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step,
@@ -355,11 +378,11 @@ def run_ours(args):
     if world == 1 and args.quick:
         pass
     elif world == 1:
-        e_ms, h2d, d2h, _ = time_e2e(hp, raw, max(3, args.steps // 4), 2)
-        e_steps = max(3, args.steps // 4)
+        e_ms, h2d, d2h, _ = time_e2e(hp, raw, min(40, max(3, args.steps // 4)), 2)
+        e_steps = min(40, max(3, args.steps // 4))
         line["e2e"] = {"value": n / (e_ms / e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / e_steps,
-                       "note": "pinned host state+actions -> device, step, obs+rew+reset -> pinned host; PCIe-bound"}
+                       "note": "pinned host state+actions -> device, step, obs+rew+reset -> pinned host; upload of step t+1 overlaps read-back of step t (3 streams); PCIe-bound"}
         del hp
         torch.cuda.empty_cache()
         sweep = []
@@ -381,7 +404,7 @@ def run_ours(args):
                                               f"{ms:.0f} ms/step; 4096 envs (BASELINE configs[0]): {rate4k:.3g} env-steps/s"}
     else:
         line_e2e = None
-        e_steps = max(3, args.steps // 4)
+        e_steps = min(40, max(3, args.steps // 4))
         e_ms, h2d, d2h, _ = time_e2e(hp, raw, e_steps, 2)
         t = torch.tensor([e_ms], device=device, dtype=torch.double)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -389,17 +412,36 @@ def run_ours(args):
             line["e2e"] = {"value": n * world / (float(t.item()) / e_steps * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print there (e.g. NCCL's version banner)
+    are sent to stderr instead."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
