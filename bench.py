@@ -198,6 +198,37 @@ def time_graph(hp, raw_actions, steps, warmup):
     return t0.elapsed_time(t1)
 
 
+def time_abb(n, device, flush, steps=50, warmup=10):
+    """BASELINE configs[3]: abb_pushbox_vision prior-stage obs/reward/reset, 65 536 envs.  ~90 B/env:
+    launch-latency-bound, so env-steps/s is reported without a roofline fraction."""
+    import torch
+    from shifu_b200 import hotpath
+    from shifu_b200.sim.synthetic import abb_snapshot
+    snap = abb_snapshot(7, 1, n, gen_device=device)
+    hp = hotpath.AbbHotPath(hotpath.abb_desc(n), root_state=snap.root.reshape(n * 4, 13).contiguous(),
+                            body_state=snap.body.reshape(n * 10, 13).contiguous(),
+                            dof_state=snap.dof.reshape(n * 6, 2).contiguous())
+    hp.ep_len.copy_(torch.randint(0, 200, (n,), device=device))
+    cube0 = hp.root_state.view(n, 4, 13)[:, 2].clone()
+    for _ in range(warmup):
+        hp.step_resident()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(steps):
+        hp.root_state.view(n, 4, 13)[:, 2].copy_(cube0)      # undo the previous step's cube resets (untimed)
+        flush.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        hp.step_resident()
+        t1.record()
+        t1.synchronize()
+        total += t0.elapsed_time(t1)
+    ms = total / steps
+    return {"envs": n, "ms_per_step_l2_flushed": ms, "env_steps_per_s": n / (ms * 1e-3),
+            "reset_fraction": float(hp.n_reset.item()) / n, "launches_per_step": 4,
+            "note": "post-physics + compaction + stats; launch-latency-bound (about 90 B/env)"}
+
+
 def time_e2e(hp, raw_actions, steps, warmup):
     """Same step through the public host API with HOST buffers: every step copies the simulator
     state + actions from pinned host memory and reads obs / reward / reset flags back."""
@@ -396,6 +427,7 @@ def run_ours(args):
                           "fused_kernel_ms": statistics.mean(km)})
             del h2
         line["sweep"] = sweep
+        line["abb_prior_stage"] = time_abb(65536, device, flush)
         if not args.no_cpu:
             rate, ms = cpu_oracle_rate(65536, steps=5, warmup=1)
             rate4k, ms4k = cpu_oracle_rate(4096, steps=20, warmup=3)
