@@ -20,7 +20,7 @@ def _install():
 
 def _make_a1(n, terrain, fused=True, carry=False):
     _install()
-    from shifu_b200.tasks.a1_conditional import A1Conditional, A1EnvConfig
+    from shifu_b200.tasks.a1_walking import A1Conditional, A1EnvConfig
     cfg = A1EnvConfig()
     cfg.num_envs = n
     cfg.device = "cuda:0"
