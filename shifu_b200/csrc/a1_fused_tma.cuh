@@ -1,19 +1,23 @@
-// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs with three warp
-// roles that never meet at a CTA-wide barrier —
+// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs (3 per SM) with
+// three warp roles that never meet at a CTA-wide barrier —
 //
-//   DMA warp (1 lane)   bulk-TMA loads of the next tiles' root/dof/contact/history/torque/action
-//                       rows (cp.async.bulk -> mbarrier), bulk-TMA stores of the finished obs tile
-//                       (32 x 259 floats, one 33 KB copy) and of the pushed history tile
-//   B group (2 warps)   lane = env: termination, reward terms + episode sums, reset (curriculum,
-//                       Philox, state rewrite), obs head, history push, carried body-frame —
-//                       the scalar "game logic" of ShifuVecEnv.post_step (env.py:93-106)
-//   C group (6 warps)   thread = scan point: the 187-point height scan of every env of the tile
-//                       (isaac_gym.py:393-433) written into the shared obs tile
+//   DMA warp (1 lane)    bulk-TMA loads (cp.async.bulk -> mbarrier, SASS UBLKCP) of the tiles'
+//                        root / dof / contact / history / torque / action rows into a
+//                        double-buffered shared-memory stage, refilled as soon as the tile's
+//                        head phase is over; bulk-TMA store of the pushed history tile
+//   B groups (2 x 2 warps, alternating tiles; lane = env)
+//                        termination, the reward-term list + episode sums, reset (curriculum,
+//                        Philox draws, state rewrite), per-step log sums — the scalar game logic
+//                        of ShifuVecEnv.post_step (env.py:93-106)
+//   scan group (6 warps; thread = scan point)
+//                        obs head from the post-reset rows (a1_conditional.py:131-144), history
+//                        push (train.py:12-14), carried body-frame velocities, then the 187-point
+//                        height scan of every env of the tile (isaac_gym.py:393-433) in batches of
+//                        8 envs with packed fp32x2 arithmetic, streamed to HBM with st.global.cs
 //
-// Tiles are double-buffered in shared memory; mbarriers hand buffers round
-// DMA -> B -> C -> DMA, so B works one to two tiles ahead of C and the global loads/stores of
-// neighbouring tiles overlap both.  Every HBM byte moves through the TMA engine in 128-byte
-// bursts; the SM only issues arithmetic, shared-memory accesses and the L1/L2 table gathers.
+// mbarriers hand a stage round DMA -> B -> scan -> DMA; every thread of the producing group
+// arrives itself, so fast warps never wait for slow siblings.  The per-env scalars the scan needs
+// travel through a 4-deep ring, which lets the B groups run ahead of the scan group.
 #pragma once
 #include "a1_fused.cuh"
 #include "f32x2.cuh"
