@@ -158,7 +158,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       // input rows are dead once the head / history phase is over: store the pushed history and
       // refill the stage right away, long before the tile's height scan finishes
-      pipe::mbar_wait<128>(&s.h_done[b], par);
+      pipe::mbar_wait<64>(&s.h_done[b], par);
       pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
       pipe::bulk_commit();
       pipe::bulk_wait_read_all();
@@ -209,7 +209,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 9; ++q) s.cla[rb][lane][q] = c9[q];
       }
-      pipe::mbar_wait<256>(&s.full_in[b], par);               // tile rows have landed
+      pipe::mbar_wait<64>(&s.full_in[b], par);                // tile rows have landed
       pipe::named_barrier(1 + g, V3_BG_THREADS);              // cla visible to both warps
 
       // ---- B1: reward terms (warp w takes terms w, w+2, ...), termination, yaw normalisation

@@ -335,6 +335,18 @@ __device__ __forceinline__ void a1_log_sums(const A1K& k, bool reset, const doub
                                             long long level_delta, int lane) {
   const unsigned any = __ballot_sync(0xffffffffu, reset);
   if (!any) return;
+  if (__popc(any) <= 4) {
+    // sparse resets (the steady state, ~1 % of envs): a handful of fire-and-forget reductions is
+    // cheaper for the latency-critical warp than seven 5-step double-precision warp reductions
+    if (reset) {
+#pragma unroll
+      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j)
+        if (j < k.n_terms) atomicAdd(k.stats + SHIFU_STAT_TERM0 + j, st_sum[j]);
+      atomicAdd(k.stats + SHIFU_STAT_NRESET, 1.0);
+      if (level_delta != 0) atomicAdd(k.stats + SHIFU_STAT_LEVEL_SUM, (double)level_delta);
+    }
+    return;
+  }
   const double cnt = warp_sum(reset ? 1.0 : 0.0);
   const double dl = warp_sum((double)level_delta);
 #pragma unroll
