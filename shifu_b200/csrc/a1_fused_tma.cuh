@@ -76,16 +76,18 @@ __device__ __forceinline__ void v3_issue_loads(V3In& in, const ShifuA1StepIO& io
 }
 
 // Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
-__device__ __noinline__ float v3_eval_term(int code, float p0, float p1, const A1K& k, const V3In& in,
+__device__ __noinline__ float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in,
                                            const float* cla, int e) {
   switch (code) {
     case SHIFU_REW_TRACKING_LIN_VEL: {
       const float dx = sub_rn(cla[0], cla[3]), dy = sub_rn(cla[1], cla[4]);
-      return mul_rn(p0, expf(div_rn(-add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), p1)));
+      const float ne = -add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+      return mul_rn(p0, expf(k.rp_pow2[q] ? mul_rn(ne, k.rp_inv[q]) : div_rn(ne, p1)));
     }
     case SHIFU_REW_TRACKING_ANG_VEL: {
       const float d = sub_rn(cla[2], cla[8]);
-      return mul_rn(p0, expf(div_rn(-mul_rn(d, d), p1)));
+      const float ne = -mul_rn(d, d);
+      return mul_rn(p0, expf(k.rp_pow2[q] ? mul_rn(ne, k.rp_inv[q]) : div_rn(ne, p1)));
     }
     case SHIFU_REW_STABILIZING_BASE:
       return add_rn(mul_rn(p0, mul_rn(cla[5], cla[5])),
@@ -107,7 +109,8 @@ __device__ __noinline__ float v3_eval_term(int code, float p0, float p1, const A
       int cnt = 0;
       for (int b = 0; b < k.n_leg; ++b) {
         const float* f = &in.contact[e][k.leg[b] * 3];
-        cnt += (norm3_fma(f[0], f[1], f[2]) > p1) ? 1 : 0;
+        // |F| > p1 tested on the sum of squares (threshold pre-squared exactly on the host)
+        cnt += (fma_rn(f[2], f[2], fma_rn(f[1], f[1], mul_rn(f[0], f[0]))) > k.rp_thr_sq[q]) ? 1 : 0;
       }
       return mul_rn(p0, (float)cnt);
     }
@@ -216,10 +219,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       bool contact_term = false;
 #pragma unroll 1
       for (int q = warp; q < k.n_terms; q += 2)
-        s.rterm[g][q][lane] = v3_eval_term(k.terms[q], k.rp[q][0], k.rp[q][1], k, in, s.cla[rb][lane], lane);
+        s.rterm[g][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, s.cla[rb][lane], lane);
       if (warp == 0) {                                                    // a1_conditional.py:146-148
         const float* fb = &in.contact[lane][k.base_body * 3];
-        contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
+        contact_term = fma_rn(fb[2], fb[2], fma_rn(fb[1], fb[1], mul_rn(fb[0], fb[0]))) > k.contact_thr_sq;
       } else {
         // heights are measured at the PRE-reset pose (isaac_gym.py:320-322 runs before post_step)
         const ScanEnv ev = make_scan_env(in.root[lane]);

@@ -41,6 +41,11 @@ struct A1K {
   float up_dist, down_factor;
   int n_terms, terms[SHIFU_MAX_REWARD_TERMS];
   float rp[SHIFU_MAX_REWARD_TERMS][2];
+  float rp_inv[SHIFU_MAX_REWARD_TERMS];   // 1/p1 when p1 is a power of two: x/p1 == x*rp_inv exactly
+  int rp_pow2[SHIFU_MAX_REWARD_TERMS];
+  // largest s with sqrt_rn(s) <= threshold: "norm > thr" == "sum of squares > thr_sq" exactly
+  float rp_thr_sq[SHIFU_MAX_REWARD_TERMS];
+  float contact_thr_sq;
   // scan table
   const short* table;     // tiled min-of-3 table
   int trows, tcols;       // valid index range: px in [0, trows-1], py in [0, tcols-1]

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
+#include <cmath>
 #include <new>
 
 #include "../../include/shifu_b200.h"
@@ -68,6 +69,16 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" const char* shifu_last_error(void) { return g_err; }
 extern "C" int shifu_abi_version(void) { return SHIFU_ABI_VERSION; }
 
+// Largest float s with sqrtf(s) <= thr (sqrtf is correctly rounded and monotonic), so that
+// "sqrt_rn(s) > thr" can be tested as "s > sqrt_threshold(thr)" with identical results.
+static float sqrt_threshold(float thr) {
+  if (!(thr >= 0.0f) || std::isinf(thr)) return thr;
+  float s = thr * thr;
+  while (s > 0.0f && std::sqrt(s) > thr) s = std::nextafter(s, 0.0f);
+  while (std::sqrt(std::nextafter(s, INFINITY)) <= thr) s = std::nextafter(s, INFINITY);
+  return s;
+}
+
 static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   if (d.abi_version != SHIFU_ABI_VERSION) return fail(SHIFU_E_RANGE, "ShifuA1Desc.abi_version %d != %d", d.abi_version, SHIFU_ABI_VERSION);
   if (d.num_envs <= 0) return fail(SHIFU_E_RANGE, "num_envs must be > 0 (got %d)", d.num_envs);
@@ -118,7 +129,16 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   k.curriculum = d.curriculum; k.max_level = d.max_terrain_level; k.n_types = d.num_terrain_types;
   k.up_dist = d.level_up_distance; k.down_factor = d.level_down_factor;
   k.n_terms = d.num_reward_terms;
-  for (int i = 0; i < d.num_reward_terms; ++i) { k.terms[i] = d.reward_terms[i]; k.rp[i][0] = d.reward_params[i][0]; k.rp[i][1] = d.reward_params[i][1]; }
+  for (int i = 0; i < d.num_reward_terms; ++i) {
+    k.terms[i] = d.reward_terms[i]; k.rp[i][0] = d.reward_params[i][0]; k.rp[i][1] = d.reward_params[i][1];
+    int ex = 0;
+    const float p1 = d.reward_params[i][1];
+    const bool pow2 = (p1 > 0.0f) && (std::frexp(p1, &ex) == 0.5f) && ex > -100 && ex < 100;
+    k.rp_pow2[i] = pow2 ? 1 : 0;
+    k.rp_inv[i] = pow2 ? 1.0f / p1 : 0.0f;
+    k.rp_thr_sq[i] = sqrt_threshold(p1);
+  }
+  k.contact_thr_sq = sqrt_threshold(d.contact_term_force);
   return SHIFU_OK;
 }
 
