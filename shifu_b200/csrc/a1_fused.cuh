@@ -210,7 +210,9 @@ a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ Sh
         if (reset) {                                                       // env.py:101-102
           float cmd[3] = {s.cla[lane][0], s.cla[lane][1], s.cla[lane][2]};
           a1_reset_env<true>(k, io, step, ge, s.root[lane], s.dof[lane], s.hist[lane], cmd, esum, len, st_sum,
-                             level_delta);
+                             level_delta, io.env_origins[ge * 3LL + 0], io.env_origins[ge * 3LL + 1],
+                             io.env_origins[ge * 3LL + 2], k.curriculum ? io.terrain_levels[ge] : 0,
+                             k.curriculum ? io.terrain_types[ge] : 0);
           s.cla[lane][0] = cmd[0]; s.cla[lane][1] = cmd[1]; s.cla[lane][2] = cmd[2];
         }
         io.ep_len[ge] = len;

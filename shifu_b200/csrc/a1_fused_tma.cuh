@@ -32,6 +32,20 @@ namespace shifu {
 #ifndef V3_CTAS_CFG
 #define V3_CTAS_CFG 3
 #endif
+#ifndef V3_POLL_B
+#define V3_POLL_B 64
+#endif
+#ifndef V3_POLL_DMA
+#define V3_POLL_DMA 64
+#endif
+#ifndef V3_POLL_SCAN
+#define V3_POLL_SCAN 32
+#endif
+#ifdef V3_PARK_NS
+#define V3_WAIT(ns, bar, par) pipe::mbar_wait_parked(bar, par, V3_PARK_NS)
+#else
+#define V3_WAIT(ns, bar, par) pipe::mbar_wait<ns>(bar, par)
+#endif
 constexpr int V3_B_GROUPS = V3_B_GROUPS_CFG;   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
 constexpr int V3_CTAS_PER_SM = V3_CTAS_CFG;
 constexpr int V3_BG_THREADS = 64, V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
@@ -44,8 +58,15 @@ struct alignas(128) V3In {            // one tile of simulator/env rows, each me
   float hist[A1_TILE][A1_DOF * A1_HIST];   // 4608 B  (pushed in place, then bulk-stored back)
   float tau[A1_TILE][A1_DOF];         //  1536 B
   float act[A1_TILE][A1_DOF];         //  1536 B
+  // per-env scalars: bulk-loaded with the rows, so the B warps issue no global loads of their own
+  long long ep_len[A1_TILE];          //   256 B
+  float cla[3][A1_TILE][3];           //  1152 B  command (rewritten on reset), base lin vel, base ang vel
+  float esum[SHIFU_MAX_REWARD_TERMS][A1_TILE];   // 1024 B  (the first n_terms rows are loaded)
+  float origin[A1_TILE][3];           //   384 B  env_origins           } read by the reset path
+  long long level[A1_TILE];           //   256 B  terrain_levels        } (curriculum only)
+  long long ttype[A1_TILE];           //   256 B  terrain_types         }
 };
-static_assert(sizeof(V3In) == 18944, "tile layout");
+static_assert(sizeof(V3In) == 22272 && offsetof(V3In, ep_len) == 18944, "tile layout");
 
 struct alignas(128) V3Smem {
   V3In in[2];
@@ -58,40 +79,74 @@ struct alignas(128) V3Smem {
   float4 sB[4][A1_TILE / 2];
   float4 sC[4][A1_TILE / 2];
   float rterm[V3_B_GROUPS][SHIFU_MAX_REWARD_TERMS][A1_TILE];
-  float cla[4][A1_TILE][9];           // command (post-reset), base lin vel, base ang vel
   uint64_t full_in[2], b_done[2], h_done[2];
+#ifdef V3_PROFILE
+  long long t_issue[2];
+#endif
 };
 
-constexpr uint32_t V3_IN_BYTES = sizeof(V3In);
+// Optional phase timers (-DV3_PROFILE, tools/prof_phases.py): one lead thread per role adds the
+// clock64() cycles it spends in each phase to v3_prof[]; never compiled into the shipped library.
+#ifdef V3_PROFILE
+__device__ unsigned long long v3_prof[32];
+#define V3_T0(lead) const bool _pl = (lead); long long _pt = clock64()
+#define V3_TICK(slot) do { const long long _n = clock64(); if (_pl) atomicAdd(&v3_prof[slot], (unsigned long long)(_n - _pt)); _pt = clock64(); } while (0)
+#define V3_COUNT(slot) do { if (_pl) atomicAdd(&v3_prof[slot], 1ull); } while (0)
+#define V3_STAMP(x) x = clock64()
+#define V3_SINCE(slot, x) do { if (_pl) atomicAdd(&v3_prof[slot], (unsigned long long)(clock64() - (x))); } while (0)
+#else
+#define V3_STAMP(x)
+#define V3_SINCE(slot, x)
+#define V3_T0(lead)
+#define V3_TICK(slot)
+#define V3_COUNT(slot)
+#endif
+
+constexpr uint32_t V3_ROW_BYTES = offsetof(V3In, ep_len);
 constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
 
-__device__ __forceinline__ void v3_issue_loads(V3In& in, const ShifuA1StepIO& io, long long e0, uint64_t* bar) {
-  pipe::mbar_arrive_expect_tx(bar, V3_IN_BYTES);
+__device__ __forceinline__ void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
+                                               uint64_t* bar) {
+  const uint32_t scalars = sizeof(in.ep_len) + sizeof(in.cla) + k.n_terms * sizeof(in.esum[0]) + sizeof(in.origin) +
+                           (k.curriculum ? sizeof(in.level) + sizeof(in.ttype) : 0);
+  pipe::mbar_arrive_expect_tx(bar, V3_ROW_BYTES + scalars);
   pipe::bulk_load(in.root, io.root_state + e0 * 13, sizeof(in.root), bar);
   pipe::bulk_load(in.dof, io.dof_state + e0 * (A1_DOF * 2), sizeof(in.dof), bar);
   pipe::bulk_load(in.contact, io.contact_state + e0 * (A1_BODIES * 3), sizeof(in.contact), bar);
   pipe::bulk_load(in.hist, io.history + e0 * (A1_DOF * A1_HIST), sizeof(in.hist), bar);
   pipe::bulk_load(in.tau, io.torques + e0 * A1_DOF, sizeof(in.tau), bar);
   pipe::bulk_load(in.act, io.actions + e0 * A1_DOF, sizeof(in.act), bar);
+  pipe::bulk_load(in.ep_len, io.ep_len + e0, sizeof(in.ep_len), bar);
+  pipe::bulk_load(in.cla[0], io.command + e0 * 3, sizeof(in.cla[0]), bar);
+  pipe::bulk_load(in.cla[1], io.base_lin_vel + e0 * 3, sizeof(in.cla[1]), bar);
+  pipe::bulk_load(in.cla[2], io.base_ang_vel + e0 * 3, sizeof(in.cla[2]), bar);
+  for (int q = 0; q < k.n_terms; ++q) pipe::bulk_load(in.esum[q], io.ep_sums[q] + e0, sizeof(in.esum[q]), bar);
+  pipe::bulk_load(in.origin, io.env_origins + e0 * 3, sizeof(in.origin), bar);
+  if (k.curriculum) {
+    pipe::bulk_load(in.level, io.terrain_levels + e0, sizeof(in.level), bar);
+    pipe::bulk_load(in.ttype, io.terrain_types + e0, sizeof(in.ttype), bar);
+  }
 }
 
 // Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
-__device__ __noinline__ float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in,
-                                           const float* cla, int e) {
+__device__ __noinline__ float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in, int e) {
+  const float* cmd = in.cla[0][e];
+  const float* lin = in.cla[1][e];
+  const float* ang = in.cla[2][e];
   switch (code) {
     case SHIFU_REW_TRACKING_LIN_VEL: {
-      const float dx = sub_rn(cla[0], cla[3]), dy = sub_rn(cla[1], cla[4]);
+      const float dx = sub_rn(cmd[0], lin[0]), dy = sub_rn(cmd[1], lin[1]);
       const float ne = -add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
       return mul_rn(p0, expf(k.rp_pow2[q] ? mul_rn(ne, k.rp_inv[q]) : div_rn(ne, p1)));
     }
     case SHIFU_REW_TRACKING_ANG_VEL: {
-      const float d = sub_rn(cla[2], cla[8]);
+      const float d = sub_rn(cmd[2], ang[2]);
       const float ne = -mul_rn(d, d);
       return mul_rn(p0, expf(k.rp_pow2[q] ? mul_rn(ne, k.rp_inv[q]) : div_rn(ne, p1)));
     }
     case SHIFU_REW_STABILIZING_BASE:
-      return add_rn(mul_rn(p0, mul_rn(cla[5], cla[5])),
-                    mul_rn(p1, add_rn(mul_rn(cla[6], cla[6]), mul_rn(cla[7], cla[7]))));
+      return add_rn(mul_rn(p0, mul_rn(lin[2], lin[2])),
+                    mul_rn(p1, add_rn(mul_rn(ang[0], ang[0]), mul_rn(ang[1], ang[1]))));
     case SHIFU_REW_SMOOTHING_ACTION: {
       float f1 = 0.0f, f2 = 0.0f;
 #pragma unroll
@@ -153,20 +208,27 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
   if (t >= V3_B_THREADS + V3_C_THREADS) {
     // ---------------- DMA warp ----------------
     if (t != V3_B_THREADS + V3_C_THREADS) return;
-    for (int j = 0; j < 2 && j < my_tiles; ++j)
-      v3_issue_loads(s.in[j], io, (long long)(first + j * stride) * A1_TILE, &s.full_in[j]);
+    for (int j = 0; j < 2 && j < my_tiles; ++j) {
+      V3_STAMP(s.t_issue[j]);
+      v3_issue_loads(s.in[j], k, io, (long long)(first + j * stride) * A1_TILE, &s.full_in[j]);
+    }
+    V3_T0(true);
     for (int j = 0; j < my_tiles; ++j) {
       const int b = j & 1;
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       // input rows are dead once the head / history phase is over: store the pushed history and
       // refill the stage right away, long before the tile's height scan finishes
-      pipe::mbar_wait<64>(&s.h_done[b], par);
+      V3_WAIT(V3_POLL_DMA, &s.h_done[b], par);
+      V3_TICK(10);
       pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
       pipe::bulk_commit();
       pipe::bulk_wait_read_all();
+      V3_STAMP(s.t_issue[b]);
       if (j + 2 < my_tiles)
-        v3_issue_loads(s.in[b], io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
+        v3_issue_loads(s.in[b], k, io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
+      V3_TICK(11);
+      V3_COUNT(12);
     }
     pipe::bulk_wait_all();                                    // global writes done before exit
     return;
@@ -176,22 +238,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     // ---------------- B groups: lane = env ----------------
     const int g = t / V3_BG_THREADS, tg = t % V3_BG_THREADS;   // group g handles tiles j = g, g+2, ...
     const int warp = tg >> 5, lane = tg & 31;
-    long long len_n = 0;
-    float c9_n[9], es_n[SHIFU_MAX_REWARD_TERMS];
-    // software-pipelined per-env scalars (warp 0 only): loaded one tile ahead
-    auto prefetch = [&](int j) {
-      const long long ge = (long long)(first + j * stride) * A1_TILE + lane;
-      len_n = io.ep_len[ge];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        c9_n[q] = io.command[ge * 3 + q];
-        c9_n[3 + q] = io.base_lin_vel[ge * 3 + q];
-        c9_n[6 + q] = io.base_ang_vel[ge * 3 + q];
-      }
-#pragma unroll
-      for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) es_n[q] = (q < k.n_terms) ? io.ep_sums[q][ge] : 0.0f;
-    };
-    if (warp == 0 && g < my_tiles) prefetch(g);
+    V3_T0(g == 0 && lane == 0);
 
     for (int j = g; j < my_tiles; j += V3_B_GROUPS) {
       const int b = j & 1;                                    // == g
@@ -199,27 +246,17 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       const long long ge = e0 + lane;
       V3In& in = s.in[b];
-      long long len = len_n;
-      float esum[SHIFU_MAX_REWARD_TERMS];
-#pragma unroll
-      for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) esum[q] = es_n[q];
-      float c9[9];
-#pragma unroll
-      for (int q = 0; q < 9; ++q) c9[q] = c9_n[q];
-      if (warp == 0 && j + V3_B_GROUPS < my_tiles) prefetch(j + V3_B_GROUPS);    // this group's next tile: scalars in flight
       const int rb = j & 3;                                   // scalar ring stage (see V3Smem)
-      if (warp == 0) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) s.cla[rb][lane][q] = c9[q];
-      }
-      pipe::mbar_wait<64>(&s.full_in[b], par);                // tile rows have landed
-      pipe::named_barrier(1 + g, V3_BG_THREADS);              // cla visible to both warps
+      V3_TICK(warp == 0 ? 0 : 4);
+      V3_WAIT(V3_POLL_B, &s.full_in[b], par);                 // tile rows + per-env scalars have landed
+      if (warp == 1) V3_SINCE(19, s.t_issue[b]);
+      V3_TICK(warp == 0 ? 1 : 5);
 
       // ---- B1: reward terms (warp w takes terms w, w+2, ...), termination, yaw normalisation
       bool contact_term = false;
 #pragma unroll 1
       for (int q = warp; q < k.n_terms; q += 2)
-        s.rterm[g][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, s.cla[rb][lane], lane);
+        s.rterm[g][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane);
       if (warp == 0) {                                                    // a1_conditional.py:146-148
         const float* fb = &in.contact[lane][k.base_body * 3];
         contact_term = fma_rn(fb[2], fb[2], fma_rn(fb[1], fb[1], mul_rn(fb[0], fb[0]))) > k.contact_thr_sq;
@@ -234,7 +271,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         bb[sl] = ev.w; bb[2 + sl] = ev.x;
         cc[sl] = ev.y;
       }
+      V3_TICK(warp == 0 ? 2 : 6);
       pipe::named_barrier(1 + g, V3_BG_THREADS);
+      V3_TICK(warp == 0 ? 3 : 7);
 
       // ---- B2: warp 0 — ordered accumulation, flags, reset, log sums
       if (warp == 0) {
@@ -242,7 +281,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) st_sum[q] = 0.0;
         long long level_delta = 0;
-        len += 1;                                                          // env.py:95
+        long long len = in.ep_len[lane] + 1;                               // env.py:95
+        float esum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+        for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) esum[q] = (q < k.n_terms) ? in.esum[q][lane] : 0.0f;
         const bool time_out = len > k.max_len;                             // a1_conditional.py:149
         const bool reset = contact_term | time_out;
         float rew = 0.0f;                                                  // env.py:180-185
@@ -259,10 +301,11 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         io.time_out_buf[ge] = time_out ? 1 : 0;
         io.contact_term_buf[ge] = contact_term ? 1 : 0;
         if (reset) {                                                       // env.py:101-102
-          float cmd[3] = {s.cla[rb][lane][0], s.cla[rb][lane][1], s.cla[rb][lane][2]};
+          float cmd[3] = {in.cla[0][lane][0], in.cla[0][lane][1], in.cla[0][lane][2]};
           a1_reset_env<true>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
-                             st_sum, level_delta);
-          s.cla[rb][lane][0] = cmd[0]; s.cla[rb][lane][1] = cmd[1]; s.cla[rb][lane][2] = cmd[2];
+                             st_sum, level_delta, in.origin[lane][0], in.origin[lane][1], in.origin[lane][2],
+                             k.curriculum ? in.level[lane] : 0, k.curriculum ? in.ttype[lane] : 0);
+          in.cla[0][lane][0] = cmd[0]; in.cla[0][lane][1] = cmd[1]; in.cla[0][lane][2] = cmd[2];
         }
         io.ep_len[ge] = len;
 #pragma unroll
@@ -274,6 +317,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       }
       // post-reset rows / command / zb are final: hand the tile to the C group
       pipe::mbar_arrive(&s.b_done[b]);
+      V3_TICK(warp == 0 ? 13 : 14);
+      V3_COUNT(warp == 0 ? 15 : 31);
     }
     return;
   }
@@ -289,12 +334,14 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     const f2_t BX = pk(bx, bx), BY = pk(by, by), NBY = pk(-by, -by), BORDER = pk(k.border, k.border);
     const f2_t RCP = pk(k.hdiv.r, k.hdiv.r), NEGD = pk(-k.hdiv.d, -k.hdiv.d), VS = pk(k.vscale, k.vscale);
     const f2_t NZ = pk(k.neg_zero, k.neg_zero);
+    V3_T0(p == 0);
     for (int j = 0; j < my_tiles; ++j) {
       const int b = j & 1;
       const uint32_t par = (j >> 1) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       const int rb = j & 3;
-      pipe::mbar_wait(&s.b_done[b], par);
+      V3_WAIT(V3_POLL_SCAN, &s.b_done[b], par);
+      V3_TICK(16);
       // ---- obs head (a1_conditional.py:131-144) + history push (train.py:12-14): post-reset rows
       {
         V3In& in = s.in[b];
@@ -316,7 +363,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         }
         for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
           const int e = i / 12, q = i - e * 12;
-          const float v = (q < 9) ? s.cla[rb][e][q] : ((q == 11) ? -1.0f : 0.0f);
+          const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
           __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
         }
         // carried body-frame velocities for the next control step (robot.py:222-229, D7)
@@ -336,6 +383,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       }
       pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
       pipe::mbar_arrive(&s.h_done[b]);
+      V3_TICK(9);
       if (p < A1_POINTS) {
         float* orow = io.obs_buf + e0 * A1_OBS + A1_HEAD + p;
         float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
@@ -406,6 +454,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           }
         }
       }
+      V3_TICK(17);
+      V3_COUNT(18);
     }
   }
 }

@@ -266,22 +266,22 @@ __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& 
                                              float* root_row, float* dof_row, float* hist_row,
                                              float (&cmd)[3], float (&esum)[SHIFU_MAX_REWARD_TERMS],
                                              long long& len, double (&st_sum)[SHIFU_MAX_REWARD_TERMS],
-                                             long long& level_delta) {
+                                             long long& level_delta, float ox, float oy, float oz,
+                                             long long old_level, long long ty) {
+  // (ox, oy, oz) = env_origins[ge], old_level = terrain_levels[ge], ty = terrain_types[ge]: read by
+  // the caller (global memory, or the shared-memory stage the pipelined kernel bulk-loads them into)
   const long long gid = k.env_offset + ge;
-  float ox = io.env_origins[ge * 3LL + 0], oy = io.env_origins[ge * 3LL + 1], oz = io.env_origins[ge * 3LL + 2];
   if (k.curriculum) {                                                    // a1_conditional.py:204-221
     const float dist = norm2_fma(sub_rn(root_row[0], ox), sub_rn(root_row[1], oy));
     const bool up = dist > k.up_dist;
     const float need = mul_rn(mul_rn(norm2_fma(cmd[0], cmd[1]), k.max_len_s), k.down_factor);
     const bool down = (dist < need) && !up;
-    const long long old_level = io.terrain_levels[ge];
     long long level = old_level + (up ? 1 : 0) - (down ? 1 : 0);
     const long long rnd = randint(draw(k.seed, gid, step, STREAM_LEVEL).x, k.max_level);
     level = (level >= k.max_level) ? rnd : (level < 0 ? 0 : level);
     io.terrain_levels[ge] = level;
     level_delta = level - old_level;
-    const long long ty = io.terrain_types[ge];                           // isaac_gym.py:387-391
-    const float* org = io.terrain_origins + (level * k.n_types + ty) * 3;
+    const float* org = io.terrain_origins + (level * k.n_types + ty) * 3;   // isaac_gym.py:387-391
     ox = org[0]; oy = org[1]; oz = org[2];
     io.env_origins[ge * 3LL + 0] = ox; io.env_origins[ge * 3LL + 1] = oy; io.env_origins[ge * 3LL + 2] = oz;
   }
@@ -393,7 +393,9 @@ a1_reset_idx_kernel(const __grid_constant__ A1K k, const __grid_constant__ Shifu
         long long len = 0;
         a1_reset_env<false>(k, io, step, ge, io.root_state + ((long long)ge * k.root_stride + k.root_offset) * 13,
                             io.dof_state + (long long)ge * (A1_DOF * 2),
-                            io.history + (long long)ge * (A1_DOF * A1_HIST), cmd, esum, len, st_sum, level_delta);
+                            io.history + (long long)ge * (A1_DOF * A1_HIST), cmd, esum, len, st_sum, level_delta,
+                            io.env_origins[ge * 3LL + 0], io.env_origins[ge * 3LL + 1], io.env_origins[ge * 3LL + 2],
+                            k.curriculum ? io.terrain_levels[ge] : 0, k.curriculum ? io.terrain_types[ge] : 0);
         io.ep_len[ge] = 0;
         io.reset_buf[ge] = 1;
 #pragma unroll

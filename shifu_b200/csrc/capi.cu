@@ -69,6 +69,19 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" const char* shifu_last_error(void) { return g_err; }
 extern "C" int shifu_abi_version(void) { return SHIFU_ABI_VERSION; }
 
+#ifdef V3_PROFILE
+// dev-only (tools/prof_phases.py): read and optionally clear the fused kernel's phase timers
+extern "C" int shifu_debug_profile(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, shifu::v3_prof, sizeof(unsigned long long) * 32);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[32] = {};
+    e = cudaMemcpyToSymbol(shifu::v3_prof, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif
+
 // Largest float s with sqrtf(s) <= thr (sqrtf is correctly rounded and monotonic), so that
 // "sqrt_rn(s) > thr" can be tested as "s > sqrt_threshold(thr)" with identical results.
 static float sqrt_threshold(float thr) {
@@ -365,7 +378,10 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool can_tma = c->use_tma && c->a1k.root_stride == 1 && c->a1k.root_offset == 0 && al16(io->root_state) &&
                        al16(io->dof_state) && al16(io->contact_state) && al16(io->history) && al16(io->torques) &&
-                       al16(io->actions) && al16(io->obs_buf);
+                       al16(io->actions) && al16(io->obs_buf) && al16(io->ep_len) && al16(io->command) &&
+                       al16(io->base_lin_vel) && al16(io->base_ang_vel) && al16(io->env_origins) &&
+                       (!c->a1k.curriculum || (al16(io->terrain_levels) && al16(io->terrain_types))) &&
+                       [&] { for (int q = 0; q < c->a1k.n_terms; ++q) if (!al16(io->ep_sums[q])) return false; return true; }();
   const int full_tiles = can_tma ? n / A1_TILE : 0;
   if (full_tiles > 0) {
     const int cap = c->sm_count * (c->tma_occ > 0 ? c->tma_occ : 1);
