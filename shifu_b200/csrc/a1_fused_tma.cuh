@@ -27,7 +27,7 @@ namespace shifu {
 
 // two B groups of 2 warps each: group g owns the tiles (and shared-memory buffers) of parity g
 #ifndef V3_B_GROUPS_CFG
-#define V3_B_GROUPS_CFG 2
+#define V3_B_GROUPS_CFG 1
 #endif
 #ifndef V3_CTAS_CFG
 #define V3_CTAS_CFG 3
@@ -182,7 +182,7 @@ __device__ __noinline__ float v3_eval_term(int code, int q, float p0, float p1, 
 
 // Processes tiles [0, num_tiles) of 32 envs each (the ragged tail, if any, is a separate launch of
 // the barrier-phased kernel).  Requires root_stride == 1 and 16-byte aligned tensors.
-template <bool TILED, bool EXACT_DIV>
+template <bool EXACT_DIV, bool HAS_MROW>
 __global__ void __launch_bounds__(V3_THREADS, V3_CTAS_PER_SM)
 a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -329,7 +329,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     const float bx = k.px[p % A1_NX], by = k.py[(p / A1_NX) % A1_NY];
     const float hclip = fminf(k.h_clip, k.clip_obs);         // clip(clip(v,+-a),+-b) == clip(v,+-min(a,b))
     const unsigned max_px = (unsigned)(k.trows - 1), max_py = (unsigned)(k.tcols - 1);
-    const unsigned tiles_y = (unsigned)k.tiles_y, tcols = (unsigned)k.tcols;
+    // tiled index: ((px>>3)*tiles_y + (py>>3))*64 + (px&7)*8 + (py&7)
+    //            == (px & ~7)*8*(tiles_y-1) + 8*px  +  (py & ~7)*7 + py          (5 integer ops)
+    const unsigned c1 = 8u * (unsigned)(k.tiles_y - 1);
     const short* __restrict__ table = k.table;
     const f2_t BX = pk(bx, bx), BY = pk(by, by), NBY = pk(-by, -by), BORDER = pk(k.border, k.border);
     const f2_t RCP = pk(k.hdiv.r, k.hdiv.r), NEGD = pk(-k.hdiv.d, -k.hdiv.d), VS = pk(k.vscale, k.vscale);
@@ -385,20 +387,20 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       pipe::mbar_arrive(&s.h_done[b]);
       V3_TICK(9);
       if (p < A1_POINTS) {
-        float* orow = io.obs_buf + e0 * A1_OBS + A1_HEAD + p;
-        float* mrow = (io.measured_heights != nullptr) ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
-        // 8 envs (4 pairs) per batch: all index arithmetic first (packed fp32x2, two envs per
-        // instruction), then the 8 table gathers back to back, then the 8 results.
-#pragma unroll 1
-        for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
-          int idx[8];
-          f2_t ZB[4];
+        float* ob = io.obs_buf + e0 * A1_OBS + A1_HEAD + p;
+        float* mb = HAS_MROW ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
+        // Batches of 8 envs (4 pairs): index arithmetic in packed fp32x2 (two envs per
+        // instruction), then the 8 table gathers back to back.  The four batches of a tile are
+        // software-pipelined in registers: batch i+1's arithmetic and gathers are issued before
+        // batch i's gathered heights are consumed, so the gather latency overlaps arithmetic.
+        auto gather_batch = [&](int q0, short (&h)[8]) {
+          unsigned idx[8];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float4 a = s.sA[rb][q0 + u], bq = s.sB[rb][q0 + u], cq = s.sC[rb][q0 + u];
+            const float4 a = s.sA[rb][q0 + u], bq = s.sB[rb][q0 + u];
+            const float2 cq = *reinterpret_cast<const float2*>(&s.sC[rb][q0 + u]);
             const f2_t Z2 = pk(a.x, a.y), Z = pk(a.z, a.w), W = pk(bq.x, bq.y), X = pk(bq.z, bq.w);
             const f2_t Y = pk(cq.x, cq.y);
-            ZB[u] = pk(cq.z, cq.w);
             // quat_apply_yaw (shifu/utils/terrain.py:202-206) on (bx, by, 0):
             //   t = 2(q x b) = (-2z*by, 2z*bx);  out = (b + w*t) + q x t,  q x t = (-z*ty, z*tx)
             // Products that feed an add are written fma(a, b, -0): ptxas contracts
@@ -424,35 +426,49 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             // .long() + clip (isaac_gym.py:421-425): float->uint truncates and saturates at 0
             const unsigned px0 = min(__float2uint_rz(fx0), max_px), px1 = min(__float2uint_rz(fx1), max_px);
             const unsigned py0 = min(__float2uint_rz(fy0), max_py), py1 = min(__float2uint_rz(fy1), max_py);
-            if (TILED) {
-              idx[2 * u] = (int)((((px0 >> TILE_SHIFT) * tiles_y + (py0 >> TILE_SHIFT)) << (2 * TILE_SHIFT)) |
-                                 ((px0 & 7u) << TILE_SHIFT) | (py0 & 7u));
-              idx[2 * u + 1] = (int)((((px1 >> TILE_SHIFT) * tiles_y + (py1 >> TILE_SHIFT)) << (2 * TILE_SHIFT)) |
-                                     ((px1 & 7u) << TILE_SHIFT) | (py1 & 7u));
-            } else {
-              idx[2 * u] = (int)(px0 * tcols + py0);
-              idx[2 * u + 1] = (int)(px1 * tcols + py1);
-            }
+            idx[2 * u] = (px0 & ~7u) * c1 + ((py0 & ~7u) * 7u + py0) + (px0 << 3);
+            idx[2 * u + 1] = (px1 & ~7u) * c1 + ((py1 & ~7u) * 7u + py1) + (px1 << 3);
           }
-          short h[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) h[u] = __ldg(table + idx[u]);          // isaac_gym.py:427-431 (folded)
+        };
+        auto store_batch = [&](int q0, const short (&h)[8]) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
+            const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][q0 + u].z);
             const f2_t hg = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
             float v0, v1;
-            upk(sub2(ZB[u], hg), v0, v1);                                     // (z - 0.5) - h, a1_conditional.py:132
-            const int e = 2 * (q0 + u);
-            __stcs(orow + (long long)e * A1_OBS, clampf(v0, -hclip, hclip));
-            __stcs(orow + (long long)(e + 1) * A1_OBS, clampf(v1, -hclip, hclip));
-            if (mrow != nullptr) {
+            upk(sub2(pk(zb.x, zb.y), hg), v0, v1);                            // (z - 0.5) - h, a1_conditional.py:132
+            __stcs(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
+            __stcs(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
+            if (HAS_MROW) {
               float g0, g1;
               upk(hg, g0, g1);
-              __stcs(mrow + (long long)e * A1_POINTS, g0);
-              __stcs(mrow + (long long)(e + 1) * A1_POINTS, g1);
+              __stcs(mb + (2 * u) * A1_POINTS, g0);
+              __stcs(mb + (2 * u + 1) * A1_POINTS, g1);
             }
           }
+          ob += 8 * A1_OBS;
+          if (HAS_MROW) mb += 8 * A1_POINTS;
+        };
+#ifdef V3_NO_PIPE_SCAN
+#pragma unroll 1
+        for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
+          short h[8];
+          gather_batch(q0, h);
+          store_batch(q0, h);
         }
+#else
+        short h0[8], h1[8];
+        gather_batch(0, h0);
+        gather_batch(4, h1);
+        store_batch(0, h0);
+        gather_batch(8, h0);
+        store_batch(4, h1);
+        gather_batch(12, h1);
+        store_batch(8, h0);
+        store_batch(12, h1);
+#endif
       }
       V3_TICK(17);
       V3_COUNT(18);

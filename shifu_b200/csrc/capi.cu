@@ -243,9 +243,9 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
     c->a1_grid = tiles < cap ? tiles : cap;
     c->a1_occ = occ;
     // pipelined TMA variants: opt in to the large dynamic shared-memory footprint
-    const void* tma_variants[4] = {
-        (const void*)a1_post_physics_tma_kernel<true, false>, (const void*)a1_post_physics_tma_kernel<true, true>,
-        (const void*)a1_post_physics_tma_kernel<false, false>, (const void*)a1_post_physics_tma_kernel<false, true>};
+    const void* tma_variants[4] = {      // <EXACT_DIV, HAS_MROW>
+        (const void*)a1_post_physics_tma_kernel<false, false>, (const void*)a1_post_physics_tma_kernel<false, true>,
+        (const void*)a1_post_physics_tma_kernel<true, false>, (const void*)a1_post_physics_tma_kernel<true, true>};
     for (int v = 0; v < 4 && e == cudaSuccess; ++v) {
       e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
       if (e == cudaSuccess)
@@ -253,7 +253,7 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
     }
     int tocc = 0;
     if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, a1_post_physics_tma_kernel<true, false>, V3_THREADS,
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, a1_post_physics_tma_kernel<false, false>, V3_THREADS,
                                                         sizeof(V3Smem));
     c->tma_occ = tocc;
     const char* kern = getenv("SHIFU_A1_KERNEL");
@@ -376,7 +376,7 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
   // (contiguous root rows, 16-byte aligned tensors); the barrier-phased kernel takes the ragged
   // tail (< 32 envs) or everything when bulk copies are not possible.
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool can_tma = c->use_tma && c->a1k.root_stride == 1 && c->a1k.root_offset == 0 && al16(io->root_state) &&
+  const bool can_tma = c->use_tma && tiled && c->a1k.root_stride == 1 && c->a1k.root_offset == 0 && al16(io->root_state) &&
                        al16(io->dof_state) && al16(io->contact_state) && al16(io->history) && al16(io->torques) &&
                        al16(io->actions) && al16(io->obs_buf) && al16(io->ep_len) && al16(io->command) &&
                        al16(io->base_lin_vel) && al16(io->base_ang_vel) && al16(io->env_origins) &&
@@ -387,10 +387,11 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
     const int cap = c->sm_count * (c->tma_occ > 0 ? c->tma_occ : 1);
     const dim3 grid(full_tiles < cap ? full_tiles : cap), block(V3_THREADS);
     const size_t smem = sizeof(V3Smem);
-    if (tiled && !exact) a1_post_physics_tma_kernel<true, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    else if (tiled && exact) a1_post_physics_tma_kernel<true, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    else if (!tiled && !exact) a1_post_physics_tma_kernel<false, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    else a1_post_physics_tma_kernel<false, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    const bool mrow = io->measured_heights != nullptr;
+    if (!exact && !mrow) a1_post_physics_tma_kernel<false, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    else if (!exact && mrow) a1_post_physics_tma_kernel<false, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    else if (exact && !mrow) a1_post_physics_tma_kernel<true, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
+    else a1_post_physics_tma_kernel<true, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
     CUDA_TRY(cudaGetLastError());
   }
   const int done = full_tiles * A1_TILE;
