@@ -105,7 +105,7 @@ __device__ unsigned long long v3_prof[32];
 constexpr uint32_t V3_ROW_BYTES = offsetof(V3In, ep_len);
 constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
 
-__device__ __forceinline__ void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
+__device__ __noinline__ void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
                                                uint64_t* bar) {
   const uint32_t scalars = sizeof(in.ep_len) + sizeof(in.cla) + k.n_terms * sizeof(in.esum[0]) + sizeof(in.origin) +
                            (k.curriculum ? sizeof(in.level) + sizeof(in.ttype) : 0);
@@ -459,15 +459,18 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           store_batch(q0, h);
         }
 #else
-        short h0[8], h1[8];
-        gather_batch(0, h0);
-        gather_batch(4, h1);
-        store_batch(0, h0);
-        gather_batch(8, h0);
-        store_batch(4, h1);
-        gather_batch(12, h1);
-        store_batch(8, h0);
-        store_batch(12, h1);
+        // rolled on purpose: the loop body (one gather_batch + one store_batch) stays small enough
+        // for the instruction cache shared with the other warp roles
+        short hc[8];
+        gather_batch(0, hc);
+#pragma unroll 1
+        for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
+          short hn[8];
+          if (q0 + 4 < A1_TILE / 2) gather_batch(q0 + 4, hn);
+          store_batch(q0, hc);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) hc[u] = hn[u];
+        }
 #endif
       }
       V3_TICK(17);
