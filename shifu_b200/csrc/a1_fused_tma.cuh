@@ -1,14 +1,17 @@
 // K-main, pipelined form (the default for full 32-env tiles): persistent CTAs (3 per SM) with
 // three warp roles that never meet at a CTA-wide barrier —
 //
-//   DMA warp (1 lane)    bulk-TMA loads (cp.async.bulk -> mbarrier, SASS UBLKCP) of the tiles'
-//                        root / dof / contact / history / torque / action rows into a
-//                        double-buffered shared-memory stage, refilled as soon as the tile's
-//                        head phase is over; bulk-TMA store of the pushed history tile
-//   B groups (2 x 2 warps, alternating tiles; lane = env)
+//   DMA warp (1 lane)    bulk-TMA loads (cp.async.bulk -> mbarrier, SASS UBLKCP) of everything the
+//                        tile reads — the root / dof / contact / history / torque / action rows
+//                        and the per-env scalars (ep_len, command, carried velocities, episode
+//                        sums, env origin, terrain level / type) — into a double-buffered
+//                        shared-memory stage, refilled as soon as the tile's head phase is over;
+//                        bulk-TMA store of the pushed history tile
+//   B group (2 warps; lane = env; V3_B_GROUPS_CFG groups, one by default)
 //                        termination, the reward-term list + episode sums, reset (curriculum,
 //                        Philox draws, state rewrite), per-step log sums — the scalar game logic
-//                        of ShifuVecEnv.post_step (env.py:93-106)
+//                        of ShifuVecEnv.post_step (env.py:93-106); reads only the stage, so it
+//                        issues no global loads of its own
 //   scan group (6 warps; thread = scan point)
 //                        obs head from the post-reset rows (a1_conditional.py:131-144), history
 //                        push (train.py:12-14), carried body-frame velocities, then the 187-point
@@ -17,7 +20,7 @@
 //
 // mbarriers hand a stage round DMA -> B -> scan -> DMA; every thread of the producing group
 // arrives itself, so fast warps never wait for slow siblings.  The per-env scalars the scan needs
-// travel through a 4-deep ring, which lets the B groups run ahead of the scan group.
+// travel through a 4-deep ring, which lets the B group run ahead of the scan group.
 #pragma once
 #include "a1_fused.cuh"
 #include "f32x2.cuh"
@@ -25,7 +28,7 @@
 
 namespace shifu {
 
-// two B groups of 2 warps each: group g owns the tiles (and shared-memory buffers) of parity g
+// B groups of 2 warps each: group g owns the tiles j = g, g + V3_B_GROUPS, ... (dev knob; 1 is fastest)
 #ifndef V3_B_GROUPS_CFG
 #define V3_B_GROUPS_CFG 1
 #endif
