@@ -195,6 +195,56 @@ def test_history_add_and_clip():
     assert torch.equal(out.cpu(), torch.clip(v, -100, 100))
 
 
+def test_exact_division_variant_matches_oracle():
+    """horizontal_scale != 0.1 takes the IEEE-division instantiation of the kernels (EXACT_DIV)."""
+    from oracle import shifu_oracle as so
+    from shifu_b200.sim.synthetic import a1_snapshot
+    n = 32 * 9 + 5
+    hs, origins, types, env_origins = _terrain(n)
+    p, st = util.make_oracle_a1(n, hs, origins, types, env_origins, horizontal_scale=0.13)
+    hp = util.make_cuda_a1(n, hs, origins, types, env_origins, horizontal_scale=0.13)
+    so.a1_reset(p, st, a1_snapshot(5, 0, n, p_base=0.05))
+    hp.reset_idx(None)
+    util.cuda_a1_step(hp, a1_snapshot(5, 0, n, p_base=0.05), torch.zeros(n, 12))
+    for t in range(1, 3):
+        snap = a1_snapshot(5, t, n, p_base=0.05)
+        so.a1_step(p, st, snap.actions, snap)
+        util.cuda_a1_step(hp, snap, snap.actions)
+        util.compare_a1(util.cuda_a1_outputs(hp), util.oracle_a1_outputs(st), f"hscale0.13/s{t}")
+
+
+def test_kernel_instantiations_agree(monkeypatch):
+    """The pipelined kernel with / without measured_heights and the barrier-phased kernel are the
+    same function: bit-identical outputs on the same inputs (the bench runs without
+    measured_heights, the parity tests with)."""
+    from shifu_b200.sim.synthetic import a1_snapshot
+    n = 32 * 40 + 9
+    hs, origins, types, env_origins = _terrain(n)
+
+    def run(**kw):
+        hp = util.make_cuda_a1(n, hs, origins, types, env_origins, **kw)
+        hp.reset_idx(None)
+        util.cuda_a1_step(hp, a1_snapshot(9, 0, n, p_base=0.05), torch.zeros(n, 12))
+        hp.ep_len.copy_(torch.from_numpy(np.random.RandomState(1).randint(0, 500, size=n)))
+        outs = []
+        for t in range(1, 4):
+            snap = a1_snapshot(9, t, n, p_base=0.05)
+            util.cuda_a1_step(hp, snap, snap.actions)
+            outs.append(util.cuda_a1_outputs(hp))
+        return outs
+
+    base = run()
+    lean = run(want_measured_heights=False)
+    monkeypatch.setenv("SHIFU_A1_KERNEL", "phased")
+    phased = run()
+    for t, (a, b, c) in enumerate(zip(base, lean, phased), 1):
+        assert "measured_heights" in a and "measured_heights" not in b
+        for k, v in a.items():
+            if k in b:
+                assert np.array_equal(v, b[k]), f"no-measured-heights instantiation differs: {k} step {t}"
+            assert np.array_equal(v, c[k]), f"phased kernel differs: {k} step {t}"
+
+
 def test_full_size_properties_1m():
     """BASELINE config 3 size (1M envs): properties that need no oracle run."""
     from shifu_b200.sim.synthetic import a1_snapshot

@@ -54,10 +54,10 @@ def assert_close(name: str, got, want, exact: bool):
 # ---------------------------------------------------------------------------------------------
 
 def make_oracle_a1(n, height_samples, terrain_origins, terrain_types, env_origins, *, border_size=25,
-                   max_terrain_level=10, num_cols=20, rng_seed=0x5EED, env_offset=0):
+                   max_terrain_level=10, num_cols=20, rng_seed=0x5EED, env_offset=0, horizontal_scale=0.1):
     from oracle import shifu_oracle as so
     p = so.A1Params(n=n, border_size=border_size, max_terrain_level=max_terrain_level, num_cols=num_cols,
-                    rng_seed=rng_seed, env_offset=env_offset)
+                    rng_seed=rng_seed, env_offset=env_offset, horizontal_scale=horizontal_scale)
     st = so.a1_new_state(p, torch.as_tensor(height_samples), torch.as_tensor(terrain_origins).float(),
                          torch.as_tensor(terrain_types), torch.as_tensor(env_origins).float())
     return p, st
@@ -86,7 +86,8 @@ def oracle_a1_outputs(st) -> Dict[str, np.ndarray]:
 # ---------------------------------------------------------------------------------------------
 
 def make_cuda_a1(n, height_samples, terrain_origins, terrain_types, env_origins, *, border_size=25.,
-                 max_terrain_level=10, num_cols=20, rng_seed=0x5EED, env_offset=0, carry=False, device="cuda:0"):
+                 max_terrain_level=10, num_cols=20, rng_seed=0x5EED, env_offset=0, carry=False, device="cuda:0",
+                 horizontal_scale=0.1, want_measured_heights=True):
     from shifu_b200 import hotpath
     dev = torch.device(device)
     root = torch.zeros(n, 13, device=dev)
@@ -94,13 +95,14 @@ def make_cuda_a1(n, height_samples, terrain_origins, terrain_types, env_origins,
     dof = torch.zeros(n * 12, 2, device=dev)
     contact = torch.zeros(n * 17, 3, device=dev)
     desc = hotpath.a1_desc(n, border_size=float(border_size), max_terrain_level=max_terrain_level,
-                           num_terrain_types=num_cols, rng_seed=rng_seed, env_offset=env_offset)
+                           num_terrain_types=num_cols, rng_seed=rng_seed, env_offset=env_offset,
+                           horizontal_scale=horizontal_scale)
     hp = hotpath.A1HotPath(desc, root_state=root, dof_state=dof, contact_state=contact,
                            height_samples=torch.as_tensor(height_samples),
                            terrain_origins=torch.as_tensor(terrain_origins),
                            terrain_types=torch.as_tensor(terrain_types),
                            env_origins=torch.as_tensor(env_origins).float().to(dev).contiguous(),
-                           carry_body_frame=carry)
+                           carry_body_frame=carry, want_measured_heights=want_measured_heights)
     return hp
 
 
@@ -134,7 +136,9 @@ def cuda_a1_outputs(hp) -> Dict[str, np.ndarray]:
              command=hp.command, history=hp.history, actions=hp.actions, root_state=hp.root_state,
              dof_state=hp.dof_state, dof_targets=hp.dof_targets, rand_force=hp.rand_force,
              torques=hp.torques, base_lin_vel=hp.base_lin_vel, base_ang_vel=hp.base_ang_vel,
-             projected_gravity=hp.projected_gravity, measured_heights=hp.measured_heights)
+             projected_gravity=hp.projected_gravity)
+    if hp.measured_heights is not None:
+        d["measured_heights"] = hp.measured_heights
     for k in hp.terms:
         d["ep_sum/" + k] = hp.ep_sums[k]
     ex = hp.extras()
