@@ -224,9 +224,34 @@ def time_abb(n, device, flush, steps=50, warmup=10):
         t1.synchronize()
         total += t0.elapsed_time(t1)
     ms = total / steps
+    # row N2 (pre-physics arm action path): action -> ee goal -> damped least-squares IK, one launch
+    k = hotpath.EnvKernels(device, n)
+    jac = (torch.rand(n, 9, 6, 6, device=device) * 2 - 1) * 0.6
+    actions = torch.rand(n, 3, device=device) * 2 - 1
+    ik = lambda: k.arm_ik(body_state=hp.body_state, num_bodies=10, ee_body=6, jacobian=jac, ee_link=5,
+                          dof_state=hp.dof_state, num_dof=6, dof_targets=hp.dof_targets, actions=actions,
+                          ee_velocity=0.2, dt=0.1, min_ee_pos=(-0.2, -0.2, 0.11), max_ee_pos=(0.2, 0.2, 0.14),
+                          tar_quat=(0., 1., 0., 0.))
+    for _ in range(warmup):
+        ik()
+    torch.cuda.synchronize()
+    ik_total = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        ik()
+        t1.record()
+        t1.synchronize()
+        ik_total += t0.elapsed_time(t1)
+    ik_ms = ik_total / steps
+    ik_bytes = 28 + 144 + 24 + 12 + 24             # ee pose, 6x6 jacobian, dof_pos, action, dof_targets
     return {"envs": n, "ms_per_step_l2_flushed": ms, "env_steps_per_s": n / (ms * 1e-3),
             "reset_fraction": float(hp.n_reset.item()) / n, "launches_per_step": 4,
-            "note": "post-physics + compaction + stats; launch-latency-bound (about 90 B/env)"}
+            "note": "post-physics + compaction + stats; launch-latency-bound (about 90 B/env)",
+            "arm_ik_ms_l2_flushed": ik_ms, "arm_ik_algorithmic_gbs": ik_bytes * n / (ik_ms * 1e-3) / 1e9,
+            "arm_ik_note": "pre-physics action path (SURVEY 8f N2): goal + clamp + 6x6 damped least squares, "
+                           "232 B/env algorithmic; launch-latency-bound at this size"}
 
 
 def time_e2e(hp, raw_actions, steps, warmup):

@@ -264,6 +264,37 @@ int shifu_a1_reset_idx(ShifuCtx* ctx, const ShifuA1StepIO* io, const int64_t* en
 /* ---- row a16 -------------------------------------------------------------------------------- */
 int shifu_abb_post_physics(ShifuCtx* ctx, const ShifuAbbStepIO* io, void* stream);
 
+/* ---- row N2: the arm's PRE-physics action path --------------------------------
+ * ArmRobot.inverse_kinematics (shifu/units/robot.py:156-182; same math as the stand-alone
+ * shifu/utils/torch_utils.py:41-58): damped least squares
+ *     u = J^T (J J^T + damping^2 I)^-1 [pos_err ; orn_err],   dof_targets = dof_pos + u
+ * with orn_err = xyz(goal_quat * conj(ee_quat)) * sign(w) (robot.py:150-154, torch_utils.py:12-38).
+ * When `actions` is non-NULL the goal is built first, as AbbRobot.step does
+ * (examples/abb_pushbox_vision/a_prior_stage.py:67-73):
+ *     goal_pos = clip(ee_pos + actions * ee_velocity * dt, min_ee_pos, max_ee_pos), goal_quat = tar_quat.
+ * Floating-point row: the 6x6 system is solved by Cholesky instead of torch.inverse (LU); results
+ * agree with the reference to the conditioning of J J^T + damping^2 I (tests state the tolerance). */
+typedef struct ShifuArmIkIO {
+  const float* body_state;      /* (N*num_bodies,13) gym rigid-body state; ee pose = row ee_body, cols 0:7 */
+  const float* jacobian;        /* (N,num_links,6,num_dof) gym jacobian tensor; j_ee = [:, ee_link] (robot.py:125-128) */
+  const float* dof_state;       /* (N*num_dof,2); dof_pos = [:,0] */
+  const float* goal_pose;       /* (N,7) pos + quat(xyzw), or NULL when actions is given */
+  const float* actions;         /* (N,3) or NULL */
+  float* dof_targets;           /* w (N,num_dof) */
+  int32_t num_bodies;           /* rigid bodies per env in body_state */
+  int32_t ee_body;              /* end-effector body index inside the env */
+  int32_t num_links;            /* links per env in the jacobian tensor */
+  int32_t ee_link;              /* ee_body - 1 for a fixed-base arm (robot.py:128) */
+  int32_t num_dof;              /* 1..SHIFU_MAX_DOF */
+  float ee_velocity;            /* task_config.py:60 (0.2) */
+  float dt;                     /* env.dt = sim.dt * decimation */
+  float min_ee_pos[3];          /* task_config.py:63 */
+  float max_ee_pos[3];          /* task_config.py:64 */
+  float tar_quat[4];            /* a_prior_stage.py:70 (0,1,0,0) */
+  float damping;                /* robot.py:156 (0.05) */
+} ShifuArmIkIO;
+int shifu_arm_ik(ShifuCtx* ctx, const ShifuArmIkIO* io, int32_t num_envs, void* stream);
+
 /* ---- row a8: reset_buf.nonzero().flatten() (env.py:101) -------------------------------------
  * ids_out (N) int64 ascending, n_out device int32.  Stand-alone so user-written
  * compute_termination hooks can use it too. */

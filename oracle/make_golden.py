@@ -103,6 +103,51 @@ def gen_abb(ns, name, n, steps, seed):
     print(f"{name}: {os.path.getsize(path) / 1e3:.0f} KB, resets {[int(r['reset'].sum()) for r in rec]}")
 
 
+def arm_ik_inputs(seed, n):
+    """Seeded inputs of the arm action path: random 6x6 Jacobians (some nearly rank deficient so the
+    damping matters), end-effector poses around the ABB workspace, unit quaternions, actions."""
+    g = torch.Generator().manual_seed(seed)
+    j = (torch.rand(n, 6, 6, generator=g) * 2 - 1) * 0.6
+    j[1::8, 2] = j[1::8, 1] * (1 + 1e-3)                 # two almost parallel rows
+    j[2::8, 4] *= 1e-3                                    # one almost vanishing row
+    ee_pos = (torch.rand(n, 3, generator=g) * 2 - 1) * torch.tensor([0.25, 0.25, 0.02]) + torch.tensor([0., 0., 0.125])
+    q = torch.randn(n, 4, generator=g)
+    q = q / q.norm(dim=1, keepdim=True)
+    q[3::8] = torch.tensor([0., 1., 0., 0.])             # exactly the target orientation -> w = 0 after conj*mul
+    dof_pos = (torch.rand(n, 6, generator=g) * 2 - 1)
+    actions = (torch.rand(n, 3, generator=g) * 2 - 1)
+    gq = torch.randn(n, 4, generator=g)
+    goal = torch.cat([ee_pos + 0.05 * torch.randn(n, 3, generator=g), gq / gq.norm(dim=1, keepdim=True)], dim=1)
+    return dict(j_ee=j, ee_pose=torch.cat([ee_pos, q], dim=1), dof_pos=dof_pos, actions=actions, goal_pose=goal)
+
+
+def gen_arm_ik(ns, name, n, seed):
+    """Row N2: (a) AbbRobot.step of the unmodified reference env, (b) the reference's stand-alone
+    shifu.utils.torch_utils.inverse_kinematics with free goal poses."""
+    import importlib
+    env = rh.make_abb(ns, n)
+    rb = env.robot
+    d = arm_ik_inputs(seed, n)
+    ee_row = int(rb.ee_indices[0])
+    rb.body_state[:, ee_row, :7] = d["ee_pose"]            # view into the simulator tensor
+    rb.dof_pos[:] = d["dof_pos"]
+    rb.j_ee = d["j_ee"].clone()
+    rb.step(d["actions"].clone())                         # a_prior_stage.py:67-73
+    out = {"in/" + k: v.numpy() for k, v in d.items()}
+    out["out/dof_targets_step"] = rb.dof_targets.detach().numpy().copy()
+    tu = importlib.import_module("shifu.utils.torch_utils")
+    out["out/dof_targets_goal"] = tu.inverse_kinematics(
+        d["dof_pos"], d["ee_pose"][:, :3], d["ee_pose"][:, 3:7], d["goal_pose"][:, :3], d["goal_pose"][:, 3:7],
+        d["j_ee"], "cpu").numpy().copy()
+    meta = dict(name=name, n=n, seed=seed, ee_velocity=float(rb.end_effector_velocity), dt=float(rb.env.dt),
+                min_ee_pos=[float(x) for x in rb.min_ee_pos], max_ee_pos=[float(x) for x in rb.max_ee_pos],
+                tar_quat=[0., 1., 0., 0.], damping=0.05)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1e3:.0f} KB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = rh.load_reference()
@@ -111,6 +156,7 @@ def main():
     gen_a1(ns, "a1_fullmap", n=40, steps=2, terrain=None, seed=12, store_map=False,
            snap_kw=dict(p_base=0.1))
     gen_abb(ns, "abb_small", n=48, steps=4, seed=13)
+    gen_arm_ik(ns, "arm_ik", n=64, seed=14)
 
 
 if __name__ == "__main__":

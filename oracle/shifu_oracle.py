@@ -585,3 +585,50 @@ def abb_step(p: AbbParams, st: AbbState, snap):
     st.body_state.view(p.n, p.n_bodies, 13).copy_(snap.body)
     st.dof_state.view(p.n, p.n_dof, 2).copy_(snap.dof)
     return abb_post_physics(p, st)
+
+
+# ==============================================================================================
+# Row N2: the arm's pre-physics action path
+# ==============================================================================================
+def quat_mul(a, b):
+    """shifu/utils/torch_utils.py:12-31 (== isaacgym.torch_utils.quat_mul), xyzw."""
+    x1, y1, z1, w1 = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+    x2, y2, z2, w2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    ww = (z1 + x1) * (x2 + y2)
+    yy = (w1 - y1) * (w2 + z2)
+    zz = (w1 + y1) * (w2 - z2)
+    xx = ww + yy + zz
+    qq = 0.5 * (xx + (z1 - x1) * (x2 - y2))
+    w = qq - ww + (z1 - y1) * (y2 - z2)
+    x = qq - xx + (x1 + w1) * (x2 + w2)
+    y = qq - yy + (w1 - x1) * (y2 + z2)
+    z = qq - zz + (z1 + y1) * (w2 - x2)
+    return torch.stack([x, y, z, w], dim=-1)
+
+
+def quat_conjugate(a):
+    """shifu/utils/torch_utils.py:34-38."""
+    return torch.cat((-a[:, :3], a[:, -1:]), dim=-1)
+
+
+def arm_goal_from_actions(ee_pos, actions, ee_velocity, dt, min_ee_pos, max_ee_pos, tar_quat):
+    """AbbRobot.step, examples/abb_pushbox_vision/a_prior_stage.py:67-71."""
+    tar_pos = ee_pos + actions * ee_velocity * dt
+    tar_pos = torch.clip(tar_pos, torch.as_tensor(min_ee_pos, dtype=ee_pos.dtype),
+                         torch.as_tensor(max_ee_pos, dtype=ee_pos.dtype))
+    quat = torch.as_tensor(tar_quat, dtype=ee_pos.dtype).repeat((ee_pos.shape[0], 1))
+    return torch.cat([tar_pos, quat], dim=1)
+
+
+def arm_ik(dof_pos, ee_pose, j_ee, goal_pose, damping=0.05):
+    """ArmRobot.inverse_kinematics, shifu/units/robot.py:156-182 (the stand-alone
+    shifu/utils/torch_utils.py:41-58 is the same math).  Works in the dtype of its inputs: float32
+    reproduces the reference, float64 is the yardstick the CUDA test measures both against."""
+    pos_err = goal_pose[:, :3] - ee_pose[:, :3]
+    q_r = quat_mul(goal_pose[:, 3:7], quat_conjugate(ee_pose[:, 3:7]))
+    orn_err = q_r[:, 0:3] * torch.sign(q_r[:, 3]).unsqueeze(-1)
+    dpose = torch.cat([pos_err, orn_err], -1).unsqueeze(-1)
+    j_t = torch.transpose(j_ee, 1, 2)
+    lmbda = torch.eye(6, dtype=j_ee.dtype) * (damping ** 2)
+    u = (j_t @ torch.inverse(j_ee @ j_t + lmbda) @ dpose).view(dof_pos.shape[0], dof_pos.shape[1])
+    return dof_pos + u

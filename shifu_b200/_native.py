@@ -94,6 +94,17 @@ class AbbStepIO(C.Structure):
     ]
 
 
+class ArmIkIO(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("jacobian", C.c_void_p), ("dof_state", C.c_void_p),
+        ("goal_pose", C.c_void_p), ("actions", C.c_void_p), ("dof_targets", C.c_void_p),
+        ("num_bodies", C.c_int32), ("ee_body", C.c_int32), ("num_links", C.c_int32), ("ee_link", C.c_int32),
+        ("num_dof", C.c_int32), ("ee_velocity", C.c_float), ("dt", C.c_float),
+        ("min_ee_pos", C.c_float * 3), ("max_ee_pos", C.c_float * 3), ("tar_quat", C.c_float * 4),
+        ("damping", C.c_float),
+    ]
+
+
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -113,6 +124,7 @@ SIGNATURES = {
     "shifu_compact_reset_ids": [_VP, _VP, _I32, _VP, _VP, _VP],
     "shifu_history_add": [_VP, _VP, _VP, _I32, _I32, _I32, _VP],
     "shifu_clip": [_VP, _VP, _VP, _I64, _F, _VP],
+    "shifu_arm_ik": [_VP, C.POINTER(ArmIkIO), _I32, _VP],
     "shifu_a1_reset_idx": [_VP, C.POINTER(A1StepIO), _VP, _I32, _VP],
     "shifu_collect_stats": [_VP, _VP, _VP, _VP],
     "shifu_publish_extras": [_VP, _VP, _VP, _VP],

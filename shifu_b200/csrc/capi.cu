@@ -13,6 +13,7 @@
 #include "a1_fused.cuh"
 #include "a1_fused_tma.cuh"
 #include "abb_kernels.cuh"
+#include "arm_ik.cuh"
 #include "common_kernels.cuh"
 
 using namespace shifu;
@@ -454,6 +455,20 @@ extern "C" int shifu_history_add(ShifuCtx* c, float* hist, const float* x, int32
   if (n <= 0 || a <= 0 || h <= 0) return fail(SHIFU_E_RANGE, "history shape (%d,%d,%d) invalid", n, a, h);
   const long long rows = (long long)n * a;
   history_add_kernel<<<grid_for(rows, 256, c->sm_count, 8), 256, 0, S(stream)>>>(hist, x, rows, h);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_arm_ik(ShifuCtx* c, const ShifuArmIkIO* io, int32_t n, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io); REQUIRE_PTR(io->body_state); REQUIRE_PTR(io->jacobian); REQUIRE_PTR(io->dof_state);
+  REQUIRE_PTR(io->dof_targets);
+  if ((io->goal_pose == nullptr) == (io->actions == nullptr))
+    return fail(SHIFU_E_RANGE, "shifu_arm_ik: exactly one of goal_pose / actions must be given");
+  if (n <= 0) return fail(SHIFU_E_RANGE, "num_envs must be > 0");
+  if (io->num_dof < 1 || io->num_dof > SHIFU_MAX_DOF) return fail(SHIFU_E_RANGE, "num_dof=%d out of range", io->num_dof);
+  if (io->ee_body < 0 || io->ee_body >= io->num_bodies || io->ee_link < 0 || io->ee_link >= io->num_links)
+    return fail(SHIFU_E_RANGE, "end-effector body/link index out of range");
+  arm_ik_kernel<<<grid_for(n, 128, c->sm_count, 16), 128, 0, S(stream)>>>(*io, n);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }

@@ -168,6 +168,27 @@ class EnvKernels:
         nv.check(self.lib.shifu_clip(self.handle, nv.ptr(x), nv.ptr(out), x.numel(), float(c), nv.current_stream()))
         return out
 
+    def arm_ik(self, *, body_state, num_bodies: int, ee_body: int, jacobian, ee_link: int, dof_state, num_dof: int,
+               dof_targets, goal_pose=None, actions=None, ee_velocity: float = 0.0, dt: float = 0.0,
+               min_ee_pos=(0., 0., 0.), max_ee_pos=(0., 0., 0.), tar_quat=(0., 0., 0., 1.), damping: float = 0.05):
+        """Row N2: ``ArmRobot.inverse_kinematics`` (robot.py:156-182), optionally preceded by the
+        action -> end-effector goal of ``AbbRobot.step`` (a_prior_stage.py:67-71)."""
+        io = nv.ArmIkIO()
+        if not (jacobian.is_contiguous() and jacobian.dim() == 4 and jacobian.shape[2] == 6):
+            raise ValueError("jacobian must be the contiguous (N, links, 6, dofs) gym tensor")
+        io.body_state, io.jacobian, io.dof_state = nv.ptr(body_state), nv.ptr(jacobian), nv.ptr(dof_state)
+        io.goal_pose = nv.ptr(goal_pose.contiguous()) if goal_pose is not None else None
+        io.actions = nv.ptr(actions.contiguous()) if actions is not None else None
+        io.dof_targets = nv.ptr(dof_targets)
+        io.num_bodies, io.ee_body, io.num_links, io.ee_link = num_bodies, ee_body, jacobian.shape[1], ee_link
+        io.num_dof, io.ee_velocity, io.dt, io.damping = num_dof, ee_velocity, dt, damping
+        for i in range(3):
+            io.min_ee_pos[i], io.max_ee_pos[i] = float(min_ee_pos[i]), float(max_ee_pos[i])
+        for i in range(4):
+            io.tar_quat[i] = float(tar_quat[i])
+        nv.check(self.lib.shifu_arm_ik(self.handle, C.byref(io), jacobian.shape[0], nv.current_stream()))
+        return dof_targets
+
     def body_frame(self, root_state, n, stride, offset, lin, ang, pg, gvec=None):
         nv.check(self.lib.shifu_body_frame(self.handle, nv.ptr(root_state), n, stride, offset, nv.ptr(lin),
                                            nv.ptr(ang), nv.ptr(pg), nv.ptr(gvec), nv.current_stream()))

@@ -356,8 +356,12 @@ class FakeGym:
             if a.num_dofs:
                 links = a.num_bodies - 1 if a.fixed_base else a.num_bodies
                 cols = a.num_dofs if a.fixed_base else a.num_dofs + 6
-                # stride-0 expand: the Jacobian is not on the hot path, do not spend HBM on it
-                sim.jacobians[nm] = torch.zeros(1, links, 6, cols, device=dev).expand(n_env, links, 6, cols)
+                if a.fixed_base:
+                    # arms read it every step (ArmRobot.inverse_kinematics, row N2): a real tensor
+                    sim.jacobians[nm] = torch.zeros(n_env, links, 6, cols, device=dev)
+                else:
+                    # legged robots never read it on the hot path: stride-0 expand, no HBM spent
+                    sim.jacobians[nm] = torch.zeros(1, links, 6, cols, device=dev).expand(n_env, links, 6, cols)
         sim.prepared = True
 
     def acquire_dof_state_tensor(self, sim):

@@ -122,10 +122,11 @@ class AbbRobot(ArmRobot):
         self.max_ee_pos = torch.tensor(self.cfg.max_ee_pos, dtype=torch.float, device=self.device)
 
     def step(self, actions):
-        tar_pos = self.ee_pose[:, 0, :3] + actions * self.end_effector_velocity * self.env.dt
-        tar_pos = torch.clip(tar_pos, self.min_ee_pos, self.max_ee_pos)
-        tar_quat = torch.tensor([0., 1., 0., 0], device=self.device).repeat((self.env.num_envs, 1))
-        self.dof_targets[:] = self.inverse_kinematics(torch.cat([tar_pos, tar_quat], dim=1))
+        # a_prior_stage.py:67-73 — goal construction, clamp and IK in one shifu_arm_ik launch (row N2)
+        self.env.kernels().arm_ik(actions=actions, ee_velocity=self.end_effector_velocity, dt=self.env.dt,
+                                  min_ee_pos=self.cfg.min_ee_pos, max_ee_pos=self.cfg.max_ee_pos,
+                                  tar_quat=self.cfg.default_ee_quat, dof_targets=self.dof_targets,
+                                  **self._ik_layout())
         self.apply_dof_targets(self.dof_targets)
 
 
@@ -173,7 +174,7 @@ class AbbPushBox(ShifuVecEnv):
     def step(self, actions: torch.Tensor):
         k = self.isg_env.kernels()
         self.actions = k.clip(actions, self.clip_actions, out=self.actions)      # env.py:87
-        self.isg_env.step(self.actions)                                          # IK + sim (row N2: torch)
+        self.isg_env.step(self.actions)                                          # shifu_arm_ik (row N2) + sim
         self.common_step_counter += 1
         self.hot.step_counter = self.common_step_counter - 1
         self.hot.post_physics()

@@ -112,6 +112,7 @@ class ArmRobot(Robot):
         self.ee_pose_targets = torch.zeros((self.env.num_envs, 7), dtype=torch.float, device=self.device)
         jac = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, self.name))
         self.gym.refresh_jacobian_tensors(self.sim)
+        self._jacobian, self._ee_link = jac, ee[0] - 1
         self.j_ee = jac[:, ee[0] - 1]
 
     def load_to(self, env_id, env_handle, seg_id):
@@ -145,16 +146,19 @@ class ArmRobot(Robot):
         q_r = quat_mul(desired, quat_conjugate(current))
         return q_r[:, 0:3] * torch.sign(q_r[:, 3]).unsqueeze(-1)
 
-    def inverse_kinematics(self, goal_pose, damping=0.05):
-        """Damped least squares, pre-physics action path (SURVEY.md §8f row N2 — still torch)."""
-        ee = self.ee_pose
-        pos_err = goal_pose[:, :3] - ee[:, 0, :3]
-        orn_err = self.orientation_error(goal_pose[:, 3:7], ee[:, 0, 3:7])
-        dpose = torch.cat([pos_err, orn_err], -1).unsqueeze(-1)
-        jt = torch.transpose(self.j_ee, 1, 2)
-        lmbda = torch.eye(6, device=self.device) * (damping ** 2)
-        u = (jt @ torch.inverse(self.j_ee @ jt + lmbda) @ dpose).view(self.env.num_envs, self.num_dof)
-        return self.dof_pos + u
+    def _ik_layout(self):
+        n = self.env.num_envs
+        bodies = self.env.body_state.shape[0] // n
+        if self.env.dof_state.shape[0] // n != self.num_dof:
+            raise NotImplementedError("shifu_arm_ik expects the arm to own every dof of its env")
+        jac = self._jacobian if self._jacobian.is_contiguous() else self._jacobian.contiguous()
+        return dict(body_state=self.env.body_state, num_bodies=bodies, ee_body=int(self.ee_indices[0]),
+                    jacobian=jac, ee_link=self._ee_link, dof_state=self.env.dof_state, num_dof=self.num_dof)
+
+    def inverse_kinematics(self, goal_pose, damping=0.05, out=None):
+        """Damped least squares (robot.py:156-182) — SURVEY.md §8f row N2, one ``shifu_arm_ik`` launch."""
+        out = torch.empty(self.env.num_envs, self.num_dof, device=self.device) if out is None else out
+        return self.env.kernels().arm_ik(goal_pose=goal_pose, damping=damping, dof_targets=out, **self._ik_layout())
 
 
 class LeggedRobot(ArmRobot):

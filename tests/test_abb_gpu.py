@@ -80,3 +80,79 @@ def test_oracle_parity_abb(n):
         want = {k: v.numpy() for k, v in want.items()}
         util.compare_a1(got, want, f"abb n{n}/s{t}")
         assert np.array_equal(got["reset_ids"], st.reset_ids.numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# Row N2: shifu_arm_ik — floating-point kernel (6x6 damped least squares).  Tolerance: the CUDA
+# result must be as close to exact (float64) arithmetic as the reference's own float32 path is,
+# up to a factor 2, and within 3x that distance (+1e-6) of the reference's float32 output.
+# ---------------------------------------------------------------------------------------------
+def _arm_ik_cuda(d, meta, mode):
+    from shifu_b200 import hotpath
+    n = d["j_ee"].shape[0]
+    k = hotpath.EnvKernels("cuda:0", n)
+    bodies, ee_body, links, ee_link = 10, 6, 9, 5
+    body = torch.zeros(n * bodies, 13, device="cuda")
+    body.view(n, bodies, 13)[:, ee_body, :7] = d["ee_pose"].cuda()
+    jac = torch.randn(n, links, 6, 6, device="cuda")          # other links hold garbage on purpose
+    jac[:, ee_link] = d["j_ee"].cuda()
+    dof = torch.zeros(n * 6, 2, device="cuda")
+    dof.view(n, 6, 2)[:, :, 0] = d["dof_pos"].cuda()
+    dof.view(n, 6, 2)[:, :, 1] = 7.0
+    out = torch.full((n, 6), float("nan"), device="cuda")
+    kw = dict(body_state=body, num_bodies=bodies, ee_body=ee_body, jacobian=jac, ee_link=ee_link, dof_state=dof,
+              num_dof=6, dof_targets=out, damping=meta["damping"])
+    if mode == "step":
+        k.arm_ik(actions=d["actions"].cuda(), ee_velocity=meta["ee_velocity"], dt=meta["dt"],
+                 min_ee_pos=meta["min_ee_pos"], max_ee_pos=meta["max_ee_pos"], tar_quat=meta["tar_quat"], **kw)
+    else:
+        k.arm_ik(goal_pose=d["goal_pose"].cuda(), **kw)
+    return out.cpu()
+
+
+def _arm_ik_check(d, meta, mode, ref32=None):
+    from oracle import shifu_oracle as so
+    goal = (so.arm_goal_from_actions(d["ee_pose"][:, :3], d["actions"], meta["ee_velocity"], meta["dt"],
+                                     meta["min_ee_pos"], meta["max_ee_pos"], meta["tar_quat"])
+            if mode == "step" else d["goal_pose"])
+    o32 = so.arm_ik(d["dof_pos"], d["ee_pose"], d["j_ee"], goal, meta["damping"])
+    o64 = so.arm_ik(d["dof_pos"].double(), d["ee_pose"].double(), d["j_ee"].double(), goal.double(), meta["damping"])
+    got = _arm_ik_cuda(d, meta, mode)
+    assert torch.isfinite(got).all()
+    err_ref = float((o32.double() - o64).abs().max())
+    err_cuda = float((got.double() - o64).abs().max())
+    assert err_cuda <= max(2.0 * err_ref, 1e-6), (mode, err_cuda, err_ref)
+    assert float((got - o32).abs().max()) <= 3.0 * err_ref + 1e-6
+    if ref32 is not None:
+        assert float((got - torch.from_numpy(ref32)).abs().max()) <= 3.0 * err_ref + 1e-6
+
+
+@pytest.mark.parametrize("mode", ["step", "goal"])
+def test_arm_ik_matches_reference_fixture(mode):
+    import json, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "arm_ik.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    d = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in/")}
+    _arm_ik_check(d, meta, mode, ref32=z[f"out/dof_targets_{mode}"])
+
+
+@pytest.mark.parametrize("n", [1, 4099])
+def test_arm_ik_random(n):
+    from oracle.make_golden import arm_ik_inputs
+    meta = dict(ee_velocity=0.2, dt=0.1, min_ee_pos=[-0.2, -0.2, 0.11], max_ee_pos=[0.2, 0.2, 0.14],
+                tar_quat=[0., 1., 0., 0.], damping=0.05)
+    d = arm_ik_inputs(100 + n, n)
+    _arm_ik_check(d, meta, "step")
+    _arm_ik_check(d, meta, "goal")
+
+
+def test_arm_ik_argument_errors():
+    from shifu_b200 import hotpath, _native as nv
+    k = hotpath.EnvKernels("cuda:0", 4)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    kw = dict(body_state=z(4 * 2, 13), num_bodies=2, ee_body=1, jacobian=z(4, 1, 6, 6), ee_link=0,
+              dof_state=z(4 * 6, 2), num_dof=6, dof_targets=z(4, 6))
+    with pytest.raises(nv.ShifuNativeError):
+        k.arm_ik(**kw)                                        # neither goal_pose nor actions
+    with pytest.raises(nv.ShifuNativeError):
+        k.arm_ik(goal_pose=z(4, 7), **{**kw, "ee_body": 5})   # body index out of range

@@ -119,6 +119,35 @@ def test_abb_class_api_replays_golden():
         util.compare_a1(got, want, f"abb api/s{t}", skip=("dof_targets",))
 
 
+def test_abb_robot_step_uses_arm_ik_kernel():
+    """AbbRobot.step (a_prior_stage.py:67-73) through the class API == oracle restatement."""
+    import json, os
+    from oracle import shifu_oracle as so
+    _install()
+    from shifu_b200.tasks.abb_pushbox import AbbPushBox, PriorStageEnvConfig
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "arm_ik.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    d = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in/")}
+    cfg = PriorStageEnvConfig()
+    cfg.num_envs, cfg.device = meta["n"], "cuda:0"
+    env = AbbPushBox(cfg)
+    rb = env.robot
+    assert abs(float(rb.env.dt) - meta["dt"]) < 1e-9 and rb._jacobian.is_contiguous()
+    rb.body_state[:, int(rb.ee_indices[0]), :7] = d["ee_pose"].cuda()
+    rb.dof_pos[:] = d["dof_pos"].cuda()
+    rb._jacobian[:, rb._ee_link] = d["j_ee"].cuda()
+    rb.step(d["actions"].cuda())
+    want = torch.from_numpy(z["out/dof_targets_step"])
+    goal = so.arm_goal_from_actions(d["ee_pose"][:, :3], d["actions"], meta["ee_velocity"], meta["dt"],
+                                    meta["min_ee_pos"], meta["max_ee_pos"], meta["tar_quat"])
+    o64 = so.arm_ik(d["dof_pos"].double(), d["ee_pose"].double(), d["j_ee"].double(), goal.double(), meta["damping"])
+    err_ref = float((want.double() - o64).abs().max())
+    assert float((rb.dof_targets.cpu() - want).abs().max()) <= 3.0 * err_ref + 1e-6
+    # the generic entry: inverse_kinematics(goal_pose)
+    got = rb.inverse_kinematics(d["goal_pose"].cuda()).cpu()
+    assert float((got - torch.from_numpy(z["out/dof_targets_goal"])).abs().max()) <= 3.0 * err_ref + 1e-6
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly off-GPU (ShifuNativeError), never fall back to torch."""
     from shifu_b200 import _native as nv, hotpath

@@ -168,3 +168,25 @@ def test_oracle_matches_unmodified_reference_fresh_seeds():
         assert np.array_equal(sa.rew.numpy(), rec[t - 1]["rew"])
         assert np.array_equal(sa.reset.numpy().astype(np.uint8), rec[t - 1]["reset"])
         assert np.array_equal(sa.root_state.numpy(), rec[t - 1]["root_state"])
+
+
+def test_oracle_arm_ik_matches_reference_fixture():
+    """Row N2: the restated arm action path vs outputs recorded from the unmodified reference
+    (AbbRobot.step of the env, and shifu.utils.torch_utils.inverse_kinematics).  torch.inverse is
+    LAPACK: identical on the machine that made the fixture, 1e-6 elsewhere."""
+    import json
+    import os
+    from oracle import shifu_oracle as so
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "arm_ik.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    d = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in/")}
+    goal = so.arm_goal_from_actions(d["ee_pose"][:, :3], d["actions"], meta["ee_velocity"], meta["dt"],
+                                    meta["min_ee_pos"], meta["max_ee_pos"], meta["tar_quat"])
+    got = so.arm_ik(d["dof_pos"], d["ee_pose"], d["j_ee"], goal, meta["damping"]).numpy()
+    np.testing.assert_allclose(got, z["out/dof_targets_step"], rtol=1e-6, atol=1e-6)
+    got = so.arm_ik(d["dof_pos"], d["ee_pose"], d["j_ee"], d["goal_pose"], meta["damping"]).numpy()
+    np.testing.assert_allclose(got, z["out/dof_targets_goal"], rtol=1e-6, atol=1e-6)
+    # the clamp is active for some envs and inactive for others
+    raw = d["ee_pose"][:, :3] + d["actions"] * meta["ee_velocity"] * meta["dt"]
+    clamped = (goal[:, :3] != raw).any(dim=1)
+    assert 0 < int(clamped.sum()) < len(clamped)
