@@ -254,6 +254,41 @@ def time_abb(n, device, flush, steps=50, warmup=10):
                            "232 B/env algorithmic; launch-latency-bound at this size"}
 
 
+def time_camera(n, device, flush, peak, steps=20, warmup=5, h=128, w=128):
+    """CameraSensor.refresh_image_tensors for the reference's perceptual-stage
+    camera (task_config.py:124-145: 128x128, colour normalised + depth + segmentation) as one launch."""
+    import torch
+    from shifu_b200 import hotpath
+    k = hotpath.EnvKernels(device, n)
+    color = torch.randint(0, 256, (n, h, w, 4), dtype=torch.uint8, device=device)
+    depth = -torch.rand(n, h, w, device=device)
+    seg = torch.randint(0, 5, (n, h, w), dtype=torch.int32, device=device)
+    table = lambda t: (t.data_ptr() + torch.arange(n, dtype=torch.int64) * t[0].numel() * t.element_size()).to(device)
+    args = dict(height=h, width=w, normalize_color=True,
+                color=(table(color), torch.empty(n, h, w, 3, device=device)),
+                depth=(table(depth), torch.empty(n, h, w, device=device)),
+                seg=(table(seg), torch.empty(n, h, w, dtype=torch.int32, device=device)))
+    for _ in range(warmup):
+        k.camera_gather(**args)
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        k.camera_gather(**args)
+        t1.record()
+        t1.synchronize()
+        total += t0.elapsed_time(t1)
+    ms = total / steps
+    nbytes = n * h * w * (4 + 12 + 8 + 8)
+    return {"envs": n, "image": f"{h}x{w} rgba+depth+seg, colour normalised", "ms_l2_flushed": ms,
+            "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "envs_per_s": n / (ms * 1e-3),
+            "note": "one shifu_camera_gather launch replaces the reference's Python loop over the envs "
+                    "(sensors.py:165-188); 32 B/pixel"}
+
+
 def time_e2e(hp, raw_actions, steps, warmup):
     """Same step through the public host API with HOST buffers: every step copies the simulator
     state + actions from pinned host memory and reads obs / reward / reset flags back."""
@@ -453,6 +488,7 @@ def run_ours(args):
             del h2
         line["sweep"] = sweep
         line["abb_prior_stage"] = time_abb(65536, device, flush)
+        line["camera_gather"] = time_camera(2048, device, flush, peak)
         if not args.no_cpu:
             rate, ms = cpu_oracle_rate(65536, steps=5, warmup=1)
             rate4k, ms4k = cpu_oracle_rate(4096, steps=20, warmup=3)

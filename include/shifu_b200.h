@@ -295,6 +295,30 @@ typedef struct ShifuArmIkIO {
 } ShifuArmIkIO;
 int shifu_arm_ik(ShifuCtx* ctx, const ShifuArmIkIO* io, int32_t num_envs, void* stream);
 
+/* ---- row N4: CameraSensor.refresh_image_tensors ------------------------------
+ * shifu/units/sensors.py:165-188 copies one small image per env and image type inside a Python
+ * loop over the envs.  Here one launch gathers every env's per-env interop tensors (addresses in a
+ * device-resident pointer table, fixed after the sensors are created) into the batched buffers:
+ *   color  (H,W,4) u8  -> color_out (N,H,W,3) f32 = rgba[..., :3] / 255   (normalize_color,
+ *                         shifu/utils/image.py:12-15) or (N,H,W,4) u8 verbatim (sensors.py:171)
+ *   depth  (H,W) f32   -> depth_out (N,H,W) = -depth                      (sensors.py:174-177)
+ *   seg    (H,W) i32   -> seg_out   (N,H,W) verbatim                      (sensors.py:179-182)
+ *   flow   (H,W) i16   -> flow_out  (N,H,W) verbatim                      (sensors.py:184-187)
+ * A NULL *_src table skips that image type.  Every image must be 16-byte aligned. */
+typedef struct ShifuCameraGatherIO {
+  const void* const* color_src;   /* device array of N device pointers, or NULL */
+  const void* const* depth_src;
+  const void* const* seg_src;
+  const void* const* flow_src;
+  void* color_out;
+  float* depth_out;
+  int32_t* seg_out;
+  int16_t* flow_out;
+  int32_t height, width;
+  int32_t normalize_color;        /* cfg.image_normalization */
+} ShifuCameraGatherIO;
+int shifu_camera_gather(ShifuCtx* ctx, const ShifuCameraGatherIO* io, int32_t num_envs, void* stream);
+
 /* ---- row a8: reset_buf.nonzero().flatten() (env.py:101) -------------------------------------
  * ids_out (N) int64 ascending, n_out device int32.  Stand-alone so user-written
  * compute_termination hooks can use it too. */

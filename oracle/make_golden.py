@@ -148,6 +148,32 @@ def gen_arm_ik(ns, name, n, seed):
     print(f"{name}: {os.path.getsize(path) / 1e3:.0f} KB")
 
 
+def gen_camera(ns, name, n, height, width):
+    """Row N4: the unmodified CameraSensor.refresh_image_tensors, driven through
+    IsaacGymEnv.refresh_sensors (isaac_gym.py:159-170), for both image_normalization settings."""
+    from shifu_b200.sim.fake_isaacgym import synthetic_camera_image
+    types_ = [0, 1, 2, 3]
+    out = {}
+    for norm in (False, True):
+        env = rh.make_camera_env(ns, n, height, width, norm, types_)
+        env.isg_env.refresh_sensors()
+        env.isg_env.refresh_sensors()                      # second frame: the buffers are overwritten
+        frame = env.isg_env.sim.camera_frame
+        cam = env.camera
+        tag = "norm" if norm else "raw"
+        out[f"{tag}/color"] = cam.color_buf.numpy().copy()
+        out[f"{tag}/depth"] = cam.depth_buf.numpy().copy()
+        out[f"{tag}/seg"] = cam.segmentation_buf.numpy().copy()
+        out[f"{tag}/flow"] = cam.optical_flow_buf.numpy().copy()
+    for t, key in enumerate(("color", "depth", "seg", "flow")):
+        out[f"in/{key}"] = np.stack([synthetic_camera_image(e, t, frame, height, width).numpy() for e in range(n)])
+    meta = dict(name=name, n=n, height=height, width=width, frame=frame)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1e3:.0f} KB, frame {frame}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = rh.load_reference()
@@ -157,6 +183,7 @@ def main():
            snap_kw=dict(p_base=0.1))
     gen_abb(ns, "abb_small", n=48, steps=4, seed=13)
     gen_arm_ik(ns, "arm_ik", n=64, seed=14)
+    gen_camera(ns, "camera", n=5, height=8, width=24)
 
 
 if __name__ == "__main__":

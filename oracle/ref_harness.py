@@ -292,6 +292,44 @@ def make_abb(ns, n: int):
     return ns.abb.AbbPushBox(cfg)
 
 
+def make_camera_env(ns, n: int, height: int, width: int, image_normalization: bool, image_types):
+    """The reference's ABB env with a CameraSensor, built like VisionAbbPushBox.__init__
+    (examples/abb_pushbox_vision/b_regression_stage.py:34-50) from the reference's own classes."""
+    ns.fake.reset_gym()
+    ns.fake.set_default_device("cpu")
+    cfg = ns.abb_cfg.PriorStageEnvConfig()
+    cfg.num_envs = n
+    cfg.device = "cpu"
+    units = importlib.import_module("shifu.units")
+    h, w, norm, types_ = height, width, image_normalization, list(image_types)
+
+    class CamCfg(ns.abb_cfg.PushBoxCameraConfig):
+        image_types = types_
+        image_normalization = norm
+
+        class camera_props(ns.abb_cfg.PushBoxCameraConfig.camera_props):
+            width = w
+            height = h
+
+    abb = ns.abb
+
+    class VisionEnv(abb.AbbPushBox):
+        def __init__(self, cfg):
+            super(abb.AbbPushBox, self).__init__(cfg)
+            self.robot = abb.AbbRobot(ns.abb_cfg.AbbRobotConfig())
+            self.table = units.Box(ns.abb_cfg.TableConfig())
+            self.cube = abb.RandPosBox(ns.abb_cfg.PushBoxConfig())
+            self.goal = abb.GoalBox(ns.abb_cfg.GoalBoxConfig())
+            self.camera = units.CameraSensor(CamCfg())
+            self.isg_env.create_envs(robot=self.robot, objects=[self.table, self.cube, self.goal],
+                                     sensors=[self.camera])
+            self.success_buf = torch.zeros(self.num_envs, device=self.device, dtype=torch.float)
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    return VisionEnv(cfg)
+
+
 def abb_state(env) -> Dict[str, np.ndarray]:
     isg = env.isg_env
     d = dict(obs=env.obs_buf, rew=env.rew_buf, reset=env.reset_buf.to(torch.uint8),

@@ -632,3 +632,22 @@ def arm_ik(dof_pos, ee_pose, j_ee, goal_pose, damping=0.05):
     lmbda = torch.eye(6, dtype=j_ee.dtype) * (damping ** 2)
     u = (j_t @ torch.inverse(j_ee @ j_t + lmbda) @ dpose).view(dof_pos.shape[0], dof_pos.shape[1])
     return dof_pos + u
+
+
+# ==============================================================================================
+# Row N4: CameraSensor.refresh_image_tensors
+# ==============================================================================================
+def camera_refresh(color=None, depth=None, seg=None, flow=None, image_normalization=False):
+    """shifu/units/sensors.py:165-188 with normalize_color of shifu/utils/image.py:12-15.  Each
+    argument is the list of per-env image tensors Isaac Gym hands out; returns the batched buffers."""
+    out = {}
+    if color is not None:
+        rows = [(c[..., :3].to(torch.float32) / 255) if image_normalization else c for c in color]
+        out["color"] = torch.stack(rows)
+    if depth is not None:
+        out["depth"] = torch.stack([-d for d in depth])            # "Isaac gives negative depth map !"
+    if seg is not None:
+        out["seg"] = torch.stack(list(seg))
+    if flow is not None:
+        out["flow"] = torch.stack(list(flow))
+    return out

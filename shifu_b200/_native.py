@@ -105,6 +105,14 @@ class ArmIkIO(C.Structure):
     ]
 
 
+class CameraGatherIO(C.Structure):
+    _fields_ = [
+        ("color_src", C.c_void_p), ("depth_src", C.c_void_p), ("seg_src", C.c_void_p), ("flow_src", C.c_void_p),
+        ("color_out", C.c_void_p), ("depth_out", C.c_void_p), ("seg_out", C.c_void_p), ("flow_out", C.c_void_p),
+        ("height", C.c_int32), ("width", C.c_int32), ("normalize_color", C.c_int32),
+    ]
+
+
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -125,6 +133,7 @@ SIGNATURES = {
     "shifu_history_add": [_VP, _VP, _VP, _I32, _I32, _I32, _VP],
     "shifu_clip": [_VP, _VP, _VP, _I64, _F, _VP],
     "shifu_arm_ik": [_VP, C.POINTER(ArmIkIO), _I32, _VP],
+    "shifu_camera_gather": [_VP, C.POINTER(CameraGatherIO), _I32, _VP],
     "shifu_a1_reset_idx": [_VP, C.POINTER(A1StepIO), _VP, _I32, _VP],
     "shifu_collect_stats": [_VP, _VP, _VP, _VP],
     "shifu_publish_extras": [_VP, _VP, _VP, _VP],

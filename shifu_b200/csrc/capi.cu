@@ -14,6 +14,7 @@
 #include "a1_fused_tma.cuh"
 #include "abb_kernels.cuh"
 #include "arm_ik.cuh"
+#include "camera_gather.cuh"
 #include "common_kernels.cuh"
 
 using namespace shifu;
@@ -469,6 +470,24 @@ extern "C" int shifu_arm_ik(ShifuCtx* c, const ShifuArmIkIO* io, int32_t n, void
   if (io->ee_body < 0 || io->ee_body >= io->num_bodies || io->ee_link < 0 || io->ee_link >= io->num_links)
     return fail(SHIFU_E_RANGE, "end-effector body/link index out of range");
   arm_ik_kernel<<<grid_for(n, 128, c->sm_count, 16), 128, 0, S(stream)>>>(*io, n);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_camera_gather(ShifuCtx* c, const ShifuCameraGatherIO* io, int32_t n, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io);
+  if (n <= 0 || io->height <= 0 || io->width <= 0) return fail(SHIFU_E_RANGE, "num_envs, height and width must be > 0");
+  if ((io->color_src && !io->color_out) || (io->depth_src && !io->depth_out) || (io->seg_src && !io->seg_out) ||
+      (io->flow_src && !io->flow_out))
+    return fail(SHIFU_E_NULL, "shifu_camera_gather: an image type has a source table but no output buffer");
+  if (!io->color_src && !io->depth_src && !io->seg_src && !io->flow_src) return SHIFU_OK;
+  const long long px = (long long)io->height * io->width;
+  // the per-env OUTPUT bases must stay 16-byte aligned for the vector path (px % 4, px % 8 for int16)
+  if (px % 8 != 0) return fail(SHIFU_E_RANGE, "height*width=%lld must be a multiple of 8", px);
+  int bx = (int)((px / 4 + 255) / 256);
+  if (bx > 8) bx = 8;
+  const dim3 grid(bx, n < 65535 ? n : 65535);
+  camera_gather_kernel<<<grid, 256, 0, S(stream)>>>(*io, n);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }

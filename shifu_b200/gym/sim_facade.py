@@ -150,9 +150,18 @@ class IsaacGymEnv:
         gym.refresh_net_contact_force_tensor(sim)
         gym.refresh_force_sensor_tensor(sim)
 
-    def refresh_sensors(self):
+    def refresh_sensors(self):                               # isaac_gym.py:159-170
+        from shifu_b200.units.sensors import CameraSensor
         for sensor in self.sensors:
-            sensor.refresh()
+            if isinstance(sensor, CameraSensor):
+                self.gym.fetch_results(self.sim, True)
+                self.gym.step_graphics(self.sim)
+                self.gym.render_all_camera_sensors(self.sim)
+                self.gym.start_access_image_tensors(self.sim)
+                sensor.refresh()
+                self.gym.end_access_image_tensors(self.sim)
+            else:
+                sensor.refresh()
 
     def create_ground(self):
         self.up_axis_idx = 2

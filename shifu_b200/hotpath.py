@@ -189,6 +189,28 @@ class EnvKernels:
         nv.check(self.lib.shifu_arm_ik(self.handle, C.byref(io), jacobian.shape[0], nv.current_stream()))
         return dof_targets
 
+    def camera_gather(self, *, height: int, width: int, normalize_color: bool, color=None, depth=None, seg=None,
+                      flow=None):
+        """Row N4: ``CameraSensor.refresh_image_tensors`` (sensors.py:165-188) in one launch.  Each of
+        color / depth / seg / flow is ``(pointer_table, out)``: an int64 device tensor holding the N
+        per-env image addresses and the batched output buffer."""
+        io = nv.CameraGatherIO()
+        io.height, io.width, io.normalize_color = height, width, int(bool(normalize_color))
+        n = None
+        for name, pair in (("color", color), ("depth", depth), ("seg", seg), ("flow", flow)):
+            if pair is None:
+                continue
+            table, out = pair
+            if table.dtype != torch.int64 or not table.is_contiguous():
+                raise ValueError(f"{name}: the pointer table must be a contiguous int64 tensor")
+            n = table.numel() if n is None else n
+            if table.numel() != n or out.shape[0] != n or not out.is_contiguous():
+                raise ValueError(f"{name}: table / output size mismatch")
+            setattr(io, name + "_src", nv.ptr(table))
+            setattr(io, name + "_out", nv.ptr(out))
+        if n is not None:
+            nv.check(self.lib.shifu_camera_gather(self.handle, C.byref(io), n, nv.current_stream()))
+
     def body_frame(self, root_state, n, stride, offset, lin, ang, pg, gvec=None):
         nv.check(self.lib.shifu_body_frame(self.handle, nv.ptr(root_state), n, stride, offset, nv.ptr(lin),
                                            nv.ptr(ang), nv.ptr(pg), nv.ptr(gvec), nv.current_stream()))

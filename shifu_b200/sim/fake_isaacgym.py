@@ -204,12 +204,35 @@ class FakeSim:
         self.last_forces = None
         self.last_dof_forces = None
         self.last_dof_targets = None
+        # camera sensors: "rendered" frames are a seeded function of (env, image type, frame)
+        self.camera_frame = 0
+        self.camera_provider: Optional[Callable[[int, int, int, int, int], torch.Tensor]] = None
 
 
 class FakeEnv:
     def __init__(self, index: int):
         self.index = index
         self.actors: List[int] = []        # sim-domain actor indices
+        self.cameras: List[Dict] = []      # per camera: props, pose, lazily allocated image tensors
+
+
+_IMAGE_DTYPES = {0: torch.uint8, 1: torch.float32, 2: torch.int32, 3: torch.int16}   # gymapi.IMAGE_*
+
+
+def synthetic_camera_image(env_index: int, image_type: int, frame: int, height: int, width: int) -> torch.Tensor:
+    """Seeded stand-in for a rendered frame (CPU tensor): RGBA uint8, NEGATIVE depth in metres (as
+    Isaac Gym returns it), int32 segmentation ids, int16 optical flow."""
+    g = torch.Generator().manual_seed(1_000_003 * env_index + 101 * image_type + frame + 7)
+    if image_type == 0:
+        return torch.randint(0, 256, (height, width, 4), generator=g, dtype=torch.uint8)
+    if image_type == 1:
+        d = -(0.1 + 2.9 * torch.rand(height, width, generator=g))
+        d[0, 0] = 0.0                                      # -(+0.0) = -0.0 must survive the gather
+        d[0, 1 % width] = float("-inf")
+        return d
+    if image_type == 2:
+        return torch.randint(0, 5, (height, width), generator=g, dtype=torch.int32)
+    return torch.randint(-32768, 32768, (height, width), generator=g, dtype=torch.int32).to(torch.int16)
 
 
 class FakeGym:
@@ -388,6 +411,57 @@ class FakeGym:
         self._tick(sim, "simulate")
 
     def fetch_results(self, sim, wait):
+        pass
+
+    # -- camera sensors (shifu/units/sensors.py) --------------------------
+    def create_camera_sensor(self, env, props):
+        env.cameras.append(dict(props=props, images={}, location=None, transform=None))
+        return len(env.cameras) - 1
+
+    def destroy_camera_sensor(self, sim, env, cam):
+        env.cameras[cam]["images"].clear()
+
+    def set_camera_location(self, cam, env, pos, lookat):
+        env.cameras[cam]["location"] = (pos, lookat)
+
+    def set_camera_transform(self, cam, env, transform):
+        env.cameras[cam]["transform"] = transform
+
+    def get_camera_proj_matrix(self, sim, env, cam):
+        return np.eye(4, dtype=np.float32)
+
+    def get_camera_view_matrix(self, sim, env, cam):
+        return np.eye(4, dtype=np.float32)
+
+    def _render_into(self, sim, env, cam, image_type, t):
+        p = env.cameras[cam]["props"]
+        fn = sim.camera_provider or synthetic_camera_image
+        t.copy_(fn(env.index, image_type, sim.camera_frame, int(p.height), int(p.width)))
+
+    def get_camera_image_gpu_tensor(self, sim, env, cam, image_type):
+        """One persistent tensor per (env, camera, image type), like Isaac Gym's interop buffers."""
+        c = env.cameras[cam]
+        if image_type not in c["images"]:
+            h, w = int(c["props"].height), int(c["props"].width)
+            shape = (h, w, 4) if image_type == 0 else (h, w)
+            c["images"][image_type] = torch.zeros(shape, dtype=_IMAGE_DTYPES[image_type], device=sim.device)
+            self._render_into(sim, env, cam, image_type, c["images"][image_type])
+        return c["images"][image_type]
+
+    def step_graphics(self, sim):
+        pass
+
+    def render_all_camera_sensors(self, sim):
+        sim.camera_frame += 1
+        for env in sim.envs:
+            for cam, c in enumerate(env.cameras):
+                for image_type, t in c["images"].items():
+                    self._render_into(sim, env, cam, image_type, t)
+
+    def start_access_image_tensors(self, sim):
+        pass
+
+    def end_access_image_tensors(self, sim):
         pass
 
     def refresh_actor_root_state_tensor(self, sim):

@@ -13,7 +13,9 @@ import numpy as np
 import torch
 
 from shifu_b200 import hotpath
-from shifu_b200.configs import ArmRobotActorConfig, BaseEnvConfig, BoxActorConfig, PPOConfig
+from isaacgym import gymapi
+
+from shifu_b200.configs import ArmRobotActorConfig, BaseEnvConfig, BoxActorConfig, CameraSensorConfig, PPOConfig
 from shifu_b200.gym import ShifuVecEnv
 from shifu_b200.units import ArmRobot, Box
 
@@ -70,6 +72,22 @@ class AbbRobotConfig(ArmRobotActorConfig):         # task_config.py:49-64
     default_ee_quat = [0., 1., 0., 0]
     min_ee_pos = [-0.2, -0.2, 0.11]
     max_ee_pos = [0.2, 0.2, 0.14]
+
+
+class PushBoxCameraConfig(CameraSensorConfig):     # task_config.py:124-145 (RealSense D415-like)
+    name = 'rgbd_camera'
+    local_lookat_positions = [[0.7, 0., 0.7], [0., 0., 0.1]]
+    image_types = [gymapi.IMAGE_COLOR, gymapi.IMAGE_DEPTH, gymapi.IMAGE_SEGMENTATION]
+    image_normalization = True
+
+    class camera_props(CameraSensorConfig.camera_props):
+        enable_tensors = True
+        use_collision_geometry = False
+        width = 128
+        height = 128
+        horizontal_fov = 42
+        near_plane = 0.1
+        far_plane = 3
 
 
 class PriorStageEnvConfig(BaseEnvConfig):          # task_config.py:72-91
@@ -140,9 +158,14 @@ class AbbPushBox(ShifuVecEnv):
         self.table = Box(TableConfig())
         self.cube = RandPosBox(PushBoxConfig())
         self.goal = GoalBox(GoalBoxConfig())
-        self.isg_env.create_envs(robot=self.robot, objects=[self.table, self.cube, self.goal])
+        self.isg_env.create_envs(robot=self.robot, objects=[self.table, self.cube, self.goal],
+                                 sensors=self._sensors())
         self.success_buf = torch.zeros(self.num_envs, device=self.device, dtype=torch.bool)
         self._fuse()
+
+    def _sensors(self):
+        """Extra units of the perceptual stages (b_regression_stage.py:42-48); none in the prior stage."""
+        return []
 
     def _fuse(self):
         isg = self.isg_env
@@ -198,3 +221,17 @@ class AbbPushBox(ShifuVecEnv):
 
     def episode_log(self, env_ids):
         return {'success_rate': self.extras["episode"]["success_rate"]}
+
+
+class VisionAbbPushBox(AbbPushBox):
+    """The perceptual stages' env (b_regression_stage.py:34-50, c_vision_stage.py:31-47): the prior
+    stage plus an RGB-D camera per env, refreshed by ``isg_env.refresh_sensors()`` — one
+    ``shifu_camera_gather`` launch instead of a Python loop over the envs (row N4)."""
+
+    def __init__(self, cfg, camera_cfg=None, **kw):
+        from shifu_b200.units.sensors import CameraSensor
+        self.camera = CameraSensor(camera_cfg if camera_cfg is not None else PushBoxCameraConfig())
+        super().__init__(cfg, **kw)
+
+    def _sensors(self):
+        return [self.camera]

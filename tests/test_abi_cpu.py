@@ -43,7 +43,8 @@ def test_sm100a_cubin_present():
 def test_ctypes_structs_match_header_layout(tmp_path):
     from shifu_b200 import _native as nv
     structs = {"ShifuA1Desc": nv.A1Desc, "ShifuA1StepIO": nv.A1StepIO, "ShifuAbbDesc": nv.AbbDesc,
-               "ShifuAbbStepIO": nv.AbbStepIO, "ShifuArmIkIO": nv.ArmIkIO}
+               "ShifuAbbStepIO": nv.AbbStepIO, "ShifuArmIkIO": nv.ArmIkIO,
+               "ShifuCameraGatherIO": nv.CameraGatherIO}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, st in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -190,3 +190,25 @@ def test_oracle_arm_ik_matches_reference_fixture():
     raw = d["ee_pose"][:, :3] + d["actions"] * meta["ee_velocity"] * meta["dt"]
     clamped = (goal[:, :3] != raw).any(dim=1)
     assert 0 < int(clamped.sum()) < len(clamped)
+
+
+def test_oracle_camera_refresh_matches_reference_fixture():
+    """Row N4: restated CameraSensor.refresh_image_tensors vs buffers recorded from the unmodified
+    reference class driven through IsaacGymEnv.refresh_sensors (bit-exact, -0.0 and inf included)."""
+    import json
+    import os
+    from oracle import shifu_oracle as so
+    from shifu_b200.sim.fake_isaacgym import synthetic_camera_image
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    keys = ("color", "depth", "seg", "flow")
+    ins = {k: [torch.from_numpy(x) for x in z["in/" + k]] for k in keys}
+    for t, k in enumerate(keys):          # the stand-in renderer still produces the recorded frames
+        assert torch.equal(ins[k][1], synthetic_camera_image(1, t, meta["frame"], meta["height"], meta["width"]))
+    for norm, tag in ((False, "raw"), (True, "norm")):
+        got = so.camera_refresh(**ins, image_normalization=norm)
+        for k in keys:
+            want = z[f"{tag}/{k}"]
+            assert got[k].numpy().dtype == want.dtype
+            assert got[k].numpy().tobytes() == want.tobytes(), (k, tag)
+    assert np.signbit(z["norm/depth"][0, 0, 0]) and z["norm/depth"][0, 0, 0] == 0.0
