@@ -396,7 +396,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         // instruction), then the 8 table gathers back to back.  The four batches of a tile are
         // software-pipelined in registers: batch i+1's arithmetic and gathers are issued before
         // batch i's gathered heights are consumed, so the gather latency overlaps arithmetic.
-        auto gather_batch = [&](int q0, short (&h)[8]) {
+        auto gather_batch = [&](int q0, int (&h)[8]) {
           unsigned idx[8];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -435,7 +435,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 8; ++u) h[u] = __ldg(table + idx[u]);          // isaac_gym.py:427-431 (folded)
         };
-        auto store_batch = [&](int q0, const short (&h)[8]) {
+        auto store_batch = [&](int q0, const int (&h)[8]) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][q0 + u].z);
@@ -457,18 +457,18 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #ifdef V3_NO_PIPE_SCAN
 #pragma unroll 1
         for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
-          short h[8];
+          int h[8];
           gather_batch(q0, h);
           store_batch(q0, h);
         }
 #else
         // rolled on purpose: the loop body (one gather_batch + one store_batch) stays small enough
         // for the instruction cache shared with the other warp roles
-        short hc[8];
+        int hc[8];   // sign-extended int16 cells: plain register moves below, no 16-bit packing
         gather_batch(0, hc);
 #pragma unroll 1
         for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
-          short hn[8];
+          int hn[8];
           if (q0 + 4 < A1_TILE / 2) gather_batch(q0 + 4, hn);
           store_batch(q0, hc);
 #pragma unroll
