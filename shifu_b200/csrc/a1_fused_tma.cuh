@@ -108,15 +108,21 @@ __device__ unsigned long long v3_prof[32];
 constexpr uint32_t V3_ROW_BYTES = offsetof(V3In, ep_len);
 constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
 
+// with_hist = false leaves the history rows out (their stage buffer is still being read by the
+// bulk store of the pushed history); v3_issue_hist_load follows once that read has finished.
+__device__ __forceinline__ void v3_issue_hist_load(V3In& in, const ShifuA1StepIO& io, long long e0, uint64_t* bar) {
+  pipe::bulk_load(in.hist, io.history + e0 * (A1_DOF * A1_HIST), sizeof(in.hist), bar);
+}
+
 __device__ __noinline__ void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
-                                               uint64_t* bar) {
+                                               uint64_t* bar, bool with_hist) {
   const uint32_t scalars = sizeof(in.ep_len) + sizeof(in.cla) + k.n_terms * sizeof(in.esum[0]) + sizeof(in.origin) +
                            (k.curriculum ? sizeof(in.level) + sizeof(in.ttype) : 0);
   pipe::mbar_arrive_expect_tx(bar, V3_ROW_BYTES + scalars);
   pipe::bulk_load(in.root, io.root_state + e0 * 13, sizeof(in.root), bar);
   pipe::bulk_load(in.dof, io.dof_state + e0 * (A1_DOF * 2), sizeof(in.dof), bar);
   pipe::bulk_load(in.contact, io.contact_state + e0 * (A1_BODIES * 3), sizeof(in.contact), bar);
-  pipe::bulk_load(in.hist, io.history + e0 * (A1_DOF * A1_HIST), sizeof(in.hist), bar);
+  if (with_hist) v3_issue_hist_load(in, io, e0, bar);
   pipe::bulk_load(in.tau, io.torques + e0 * A1_DOF, sizeof(in.tau), bar);
   pipe::bulk_load(in.act, io.actions + e0 * A1_DOF, sizeof(in.act), bar);
   pipe::bulk_load(in.ep_len, io.ep_len + e0, sizeof(in.ep_len), bar);
@@ -213,7 +219,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     if (t != V3_B_THREADS + V3_C_THREADS) return;
     for (int j = 0; j < 2 && j < my_tiles; ++j) {
       V3_STAMP(s.t_issue[j]);
-      v3_issue_loads(s.in[j], k, io, (long long)(first + j * stride) * A1_TILE, &s.full_in[j]);
+      v3_issue_loads(s.in[j], k, io, (long long)(first + j * stride) * A1_TILE, &s.full_in[j], true);
     }
     V3_T0(true);
     for (int j = 0; j < my_tiles; ++j) {
@@ -226,10 +232,12 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       V3_TICK(10);
       pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
       pipe::bulk_commit();
-      pipe::bulk_wait_read_all();
       V3_STAMP(s.t_issue[b]);
-      if (j + 2 < my_tiles)
-        v3_issue_loads(s.in[b], k, io, (long long)(first + (j + 2) * stride) * A1_TILE, &s.full_in[b]);
+      // every other row of the stage is dead already: refill it while the store still reads hist
+      const long long en = (long long)(first + (j + 2) * stride) * A1_TILE;
+      if (j + 2 < my_tiles) v3_issue_loads(s.in[b], k, io, en, &s.full_in[b], false);
+      pipe::bulk_wait_read_all();
+      if (j + 2 < my_tiles) v3_issue_hist_load(s.in[b], io, en, &s.full_in[b]);
       V3_TICK(11);
       V3_COUNT(12);
     }
