@@ -248,10 +248,22 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
     const void* tma_variants[4] = {      // <EXACT_DIV, HAS_MROW>
         (const void*)a1_post_physics_tma_kernel<false, false>, (const void*)a1_post_physics_tma_kernel<false, true>,
         (const void*)a1_post_physics_tma_kernel<true, false>, (const void*)a1_post_physics_tma_kernel<true, true>};
+    // Ask for just enough shared memory for V3_CTAS_PER_SM resident CTAs (+1 KB the runtime reserves
+    // per CTA) and leave the rest of the 256 KB array to L1, which serves the scan-table gathers:
+    // 164 KB / 92 KB L1 measured 1.7 % faster than the maximum carve-out (228 KB / 28 KB L1).
+    int smem_sm = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    int carve = 100;
+    if (e == cudaSuccess && smem_sm > 0) {
+      const long long need = (long long)V3_CTAS_PER_SM * ((long long)sizeof(V3Smem) + 1024);
+      carve = (int)((need * 100 + smem_sm - 1) / smem_sm);
+      if (carve > 100) carve = 100;
+    }
+    if (getenv("SHIFU_CARVEOUT") != nullptr) carve = atoi(getenv("SHIFU_CARVEOUT"));
     for (int v = 0; v < 4 && e == cudaSuccess; ++v) {
       e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributePreferredSharedMemoryCarveout, getenv("SHIFU_CARVEOUT") ? atoi(getenv("SHIFU_CARVEOUT")) : 100);
+        e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
     int tocc = 0;
     if (e == cudaSuccess)
