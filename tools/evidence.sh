@@ -9,3 +9,6 @@ timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpur
   echo "## racecheck: fused A1 path (shared-memory pipeline)"; timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_a1_gpu.py -x -q -k "golden" 2>&1 | tail -4;
   echo "## racecheck: camera gather (shared-memory table)"; timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_camera_gpu.py -x -q -k "fixture" 2>&1 | tail -4 ) > gpurun_out/sanitizer.txt 2>&1
 tail -3 gpurun_out/bench_n1.err; cut -c1-300 gpurun_out/bench_n1.json; cat gpurun_out/sanitizer.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"pd_torque|a1_post|compact_ids|collect_stats|publish_extras|a1_reset|body_frame" -s 16 -c 24 --csv --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --quick --no-cpu > gpurun_out/launches.log 2>&1
+timeout 600 ncu --set full --section SourceCounters --clock-control none --import-source on -k regex:a1_post_physics_tma -s 4 -c 1 -o gpurun_out/prof_r1_final -f python tools/ncu_run.py > gpurun_out/ncu_final.log 2>&1
+tail -2 gpurun_out/ncu_final.log
