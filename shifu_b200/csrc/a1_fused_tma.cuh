@@ -326,7 +326,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             sub_rn(in.root[lane][2], k.h_off);                              // post-reset base z (D8)
         a1_log_sums(k, reset, st_sum, level_delta, lane);
       }
-      // post-reset rows / command / zb are final: hand the tile to the C group
+      // post-reset rows / command / zb are final: hand the tile to the scan group
       pipe::mbar_arrive(&s.b_done[b]);
       V3_TICK(warp == 0 ? 13 : 14);
       V3_COUNT(warp == 0 ? 15 : 31);
@@ -334,7 +334,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     return;
   }
 
-  // ---------------- C group: thread = scan point ----------------
+  // ---------------- scan group: thread = scan point ----------------
   {
     const int p = t - V3_B_THREADS;                          // 0..191, points 187..191 idle
     const float bx = k.px[p % A1_NX], by = k.py[(p / A1_NX) % A1_NY];
