@@ -19,9 +19,9 @@ Two execution modes, both CUDA-only (no CPU fallback):
 """
 from __future__ import annotations
 
-import typing
+import math
+from typing import Callable, Dict, List, Optional
 
-import numpy as np
 import torch
 from rsl_rl.env import VecEnv
 
@@ -31,41 +31,52 @@ from shifu_b200.utils.history import HistoryRecorder
 
 
 class ShifuVecEnv(VecEnv):
-    def __init__(self, cfg: BaseEnvConfig, env_offset: int = 0, num_envs_global: int = None):
+    # ------------------------------------------------------------------ construction (env.py:19-63)
+    def __init__(self, cfg: BaseEnvConfig, env_offset: int = 0, num_envs_global: Optional[int] = None):
         self.cfg = cfg
-        if isinstance(cfg, TerrainEnvConfig):
-            self.isg_env = TerrainGymEnv(cfg, env_offset=env_offset, num_envs_global=num_envs_global)
-        else:
-            self.isg_env = IsaacGymEnv(cfg)
         self.env_offset = int(env_offset)
-        self.num_envs_global = int(num_envs_global) if num_envs_global else int(cfg.num_envs)
-        self.num_envs = self.isg_env.num_envs
-        self.device = self.isg_env.device
-        self.num_obs = cfg.num_obs
-        self.num_privileged_obs = cfg.num_privileged_obs
-        self.num_actions = cfg.num_actions
-        self.clip_obs = cfg.normalization.clip_observations
-        self.clip_actions = cfg.normalization.clip_actions
+        self.num_envs_global = int(num_envs_global or cfg.num_envs)
+        terrain = isinstance(cfg, TerrainEnvConfig)
+        self.isg_env = (TerrainGymEnv(cfg, env_offset=env_offset, num_envs_global=num_envs_global) if terrain
+                        else IsaacGymEnv(cfg))
+        sim = self.isg_env
+        self.num_envs, self.device = sim.num_envs, sim.device
+        self.num_obs, self.num_privileged_obs, self.num_actions = cfg.num_obs, cfg.num_privileged_obs, cfg.num_actions
+        norm = cfg.normalization
+        self.clip_obs, self.clip_actions = norm.clip_observations, norm.clip_actions
         self.max_episode_length_s = cfg.episode_length_s
-        self.max_episode_length = np.ceil(self.max_episode_length_s / self.isg_env.dt)
-
-        n, dev = self.num_envs, self.device
-        self.actions = torch.zeros(n, self.num_actions, device=dev, dtype=torch.float, requires_grad=False)
-        self.obs_buf = torch.zeros(n, self.num_obs, device=dev, dtype=torch.float)
-        self.rew_buf = torch.zeros(n, device=dev, dtype=torch.float)
-        self.reset_buf = torch.ones(n, device=dev, dtype=torch.long)
-        self._episode_length_buf = torch.zeros(n, device=dev, dtype=torch.long)
-        self.time_out_buf = torch.zeros(n, device=dev, dtype=torch.bool)
-        self.extras = {}
-        if self.cfg.num_actions_history:
-            self.actions_recorder = HistoryRecorder(self.actions.shape, self.cfg.num_actions_history, device=dev,
-                                                    kernels=self.isg_env.kernels)
-        self.privileged_obs_buf = None if self.num_privileged_obs is None \
-            else torch.zeros(n, self.num_privileged_obs, device=dev, dtype=torch.float)
+        self.max_episode_length = float(math.ceil(self.max_episode_length_s / sim.dt))
         self.common_step_counter = 0
-        self.stats_allreduce = None            # callable(tensor) summing over ranks (sharded runs)
-        self.reward_functions = self.build_reward_functions()
+        self.stats_allreduce: Optional[Callable] = None    # sums a tensor over ranks (sharded runs)
+        self.extras: Dict = {}
+        self._allocate()
+        self.reward_functions: List[Callable] = self.build_reward_functions()
         self._prepare_reward_functions()
+
+    def _allocate(self):
+        """The VecEnv buffers.  Their addresses are handed to the kernels, so they are created once
+        and only ever written in place."""
+        def new(*shape, dtype=torch.float, fill=0):
+            return torch.full(shape, fill, device=self.device, dtype=dtype, requires_grad=False)
+
+        n = self.num_envs
+        self.actions = new(n, self.num_actions)
+        self.obs_buf = new(n, self.num_obs)
+        self.privileged_obs_buf = new(n, self.num_privileged_obs) if self.num_privileged_obs is not None else None
+        self.rew_buf = new(n)
+        self.reset_buf = new(n, dtype=torch.long, fill=1)
+        self.time_out_buf = new(n, dtype=torch.bool)
+        self._episode_length_buf = new(n, dtype=torch.long)
+        if self.cfg.num_actions_history:
+            self.actions_recorder = HistoryRecorder(self.actions.shape, self.cfg.num_actions_history,
+                                                    device=self.device, kernels=self.isg_env.kernels)
+
+    def _prepare_reward_functions(self):
+        if not self.reward_functions:
+            raise AssertionError("build_reward_functions() returned no reward term")
+        self.episode_rewards = {}
+        for term in self.reward_functions:
+            self.episode_rewards[term.__name__] = torch.zeros(self.num_envs, device=self.device, dtype=torch.float)
 
     # rsl_rl re-binds ``env.episode_length_buf = randint_like(...)`` (init_at_random_ep_len,
     # policy_runner.py:22); the kernels hold the buffer's address, so assignment copies in place.
@@ -75,15 +86,14 @@ class ShifuVecEnv(VecEnv):
 
     @episode_length_buf.setter
     def episode_length_buf(self, value):
-        if value is self._episode_length_buf:
-            return
-        self._episode_length_buf.copy_(torch.as_tensor(value, device=self.device))
+        if value is not self._episode_length_buf:
+            self._episode_length_buf.copy_(torch.as_tensor(value, device=self.device))
 
     def destroy(self):
         self.isg_env.destroy()
 
-    # -- user hooks ----------------------------------------------------------------------------
-    def build_reward_functions(self) -> typing.List:
+    # ------------------------------------------------------------------ user hooks
+    def build_reward_functions(self) -> List[Callable]:
         raise NotImplementedError
 
     def compute_observations(self):
@@ -92,38 +102,45 @@ class ShifuVecEnv(VecEnv):
     def compute_termination(self):
         raise NotImplementedError
 
-    def episode_log(self, env_ids) -> typing.Dict:
-        pass
+    def episode_log(self, env_ids) -> Optional[Dict]:
+        return None
 
-    # -- orchestration (user-hook mode) ----------------------------------------------------------
+    # ------------------------------------------------------------------ orchestration, user-hook mode
     def step(self, actions: torch.Tensor):
         assert self.isg_env.robot, "add robot before step"
-        k = self.isg_env.kernels()
-        self.actions = k.clip(actions, self.clip_actions, out=self.actions)      # env.py:87
+        kernels = self.isg_env.kernels()
+        kernels.clip(actions, self.clip_actions, out=self.actions)               # env.py:87
         self.isg_env.step(self.actions)
         self.post_step()
-        self.obs_buf = k.clip(self.obs_buf, self.clip_obs)                       # env.py:90
+        self.obs_buf = kernels.clip(self.obs_buf, self.clip_obs)                 # env.py:90
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
-    def post_step(self):
+    def post_step(self):                                                         # env.py:93-106
         self._episode_length_buf += 1
         self.common_step_counter += 1
         self.compute_termination()
         self.compute_reward()
-        env_ids = self.isg_env.kernels().nonzero(self.reset_buf)                 # env.py:101
-        self.reset_idx(env_ids)
+        self.reset_idx(self.isg_env.kernels().nonzero(self.reset_buf))           # env.py:101, compaction kernel
         self.compute_observations()
         self.isg_env.refresh_sensors()
         if self.cfg.num_actions_history:
             self.actions_recorder.add(self.actions)
 
-    def reset(self):
-        self.reset_idx(torch.arange(self.num_envs, device=self.device))
-        obs, pri_obs, _, _, _ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device,
-                                                      requires_grad=False))
-        return obs, pri_obs
+    def compute_reward(self):                                                    # env.py:180-185
+        self.rew_buf.zero_()
+        for term in self.reward_functions:
+            value = term()
+            self.episode_rewards[term.__name__] += value
+            self.rew_buf += value
 
-    def reset_idx(self, env_ids):
+    def reset(self):
+        everyone = torch.arange(self.num_envs, device=self.device)
+        self.reset_idx(everyone)
+        idle = torch.zeros(self.num_envs, self.num_actions, device=self.device, requires_grad=False)
+        obs, privileged, *_ = self.step(idle)
+        return obs, privileged
+
+    def reset_idx(self, env_ids):                                                # env.py:114-130
         if len(env_ids) == 0:
             return
         self.isg_env.reset_idx(env_ids)
@@ -136,25 +153,12 @@ class ShifuVecEnv(VecEnv):
         if self.cfg.send_timeouts:
             self.extras["time_outs"] = self.time_out_buf
 
-    def log_info(self, env_ids):
-        for key in self.episode_rewards.keys():
-            self.extras["episode"][key] = torch.mean(self.episode_rewards[key][env_ids]) / self.max_episode_length_s
-            self.episode_rewards[key][env_ids] = 0.
-        ep_info = self.episode_log(env_ids)
-        if ep_info:
-            self.extras["episode"].update(ep_info)
-
-    def _prepare_reward_functions(self):
-        assert len(self.reward_functions) > 0
-        self.episode_rewards = {fn.__name__: torch.zeros(self.num_envs, device=self.device, dtype=torch.float)
-                                for fn in self.reward_functions}
-
-    def compute_reward(self):
-        self.rew_buf[:] = 0.
-        for rew_func in self.reward_functions:
-            rew = rew_func()
-            self.episode_rewards[rew_func.__name__] += rew
-            self.rew_buf[:] += rew
+    def log_info(self, env_ids):                                                 # env.py:149-158
+        log = self.extras["episode"]
+        for name, sums in self.episode_rewards.items():
+            log[name] = torch.mean(sums[env_ids]) / self.max_episode_length_s
+            sums[env_ids] = 0.
+        log.update(self.episode_log(env_ids) or {})
 
     def get_observations(self):
         return self.obs_buf

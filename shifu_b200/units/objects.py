@@ -9,18 +9,21 @@ from .base import Actor
 
 
 class Object(Actor):
+    """Static scene object."""
     cfg: ActorConfig
 
 
 class Box(Object):
+    """Procedural box: its asset comes from ``gym.create_box`` instead of a URDF."""
     cfg: BoxActorConfig
 
     def create_asset(self):
-        w, h, d = self.cfg.box_dim
-        self.asset = self.gym.create_box(self.sim, w, h, d, self.asset_options)
+        width, height, depth = self.cfg.box_dim
+        self.asset = self.gym.create_box(self.sim, width, height, depth, self.asset_options)
 
     def load_to(self, env_id, env_handle, seg_id):
         super().load_to(env_id, env_handle, seg_id)
-        self.set_asset_rigid_properties(env_handle, mass=self.cfg.mass, friction=self.cfg.friction)
-        self.gym.set_rigid_body_color(env_handle, self.actor_handle, 0, gymapi.MESH_VISUAL_AND_COLLISION,
-                                      gymapi.Vec3(*self.cfg.color))
+        cfg = self.cfg
+        self.set_asset_rigid_properties(env_handle, friction=cfg.friction, mass=cfg.mass)
+        tint, whole_body = gymapi.Vec3(*cfg.color), 0
+        self.gym.set_rigid_body_color(env_handle, self.actor_handle, whole_body, gymapi.MESH_VISUAL_AND_COLLISION, tint)

@@ -2,8 +2,9 @@
 
 State views (``dof_pos``, ``dof_vel``, ``contact_forces``, ``body_state``, ``ee_pose`` ...) are
 views / gathers of the simulator's flat tensors exactly as in the reference (robot.py:48-53,
-138-154, 195-215); the per-step arithmetic that the reference does here in torch —
-``LeggedRobot.post_step`` (robot.py:222-229) — runs as a CUDA kernel (``shifu_body_frame``).
+138-154, 195-215); the per-step arithmetic the reference does here in torch runs as CUDA kernels:
+``LeggedRobot.post_step`` (robot.py:222-229) -> ``shifu_body_frame``,
+``ArmRobot.inverse_kinematics`` (robot.py:156-182) -> ``shifu_arm_ik``.
 """
 from __future__ import annotations
 
@@ -14,29 +15,25 @@ from shifu_b200.configs import ActorConfig, ArmRobotActorConfig, LeggedRobotActo
 from .base import Actor
 
 
-def _t(x, device, dtype=torch.float):
-    return torch.as_tensor(x, dtype=dtype, device=device)
+def _tensor(values, device, dtype=torch.float):
+    return torch.as_tensor(values, dtype=dtype, device=device)
 
 
 class Robot(Actor):
     cfg: ActorConfig
 
-    def reset_idx(self, env_ids):
-        self._reset_dof_state(env_ids)
-        self._reset_root_state(env_ids)
+    # dof property column -> attribute published as a device tensor (robot.py:35-45)
+    _LIMIT_COLUMNS = (("lower", "dof_lower_limits"), ("upper", "dof_upper_limits"),
+                      ("velocity", "dof_vel_limits"), ("effort", "torque_limits"))
 
-    def step(self, actions):
-        self._internal_motor_step(actions)
-
+    # ---------------------------------------------------------------- construction
     def _init_props(self):
         super()._init_props()
-        self.dof_props['driveMode'][:] = self.asset_options.default_dof_drive_mode
-        self.dof_props['stiffness'] = self.cfg.dof_stiffness
-        self.dof_props['damping'] = self.cfg.dof_damping
-        self.dof_lower_limits = _t(self.dof_props['lower'], self.device)
-        self.dof_upper_limits = _t(self.dof_props['upper'], self.device)
-        self.dof_vel_limits = _t(self.dof_props['velocity'], self.device)
-        self.torque_limits = _t(self.dof_props['effort'], self.device)
+        props = self.dof_props
+        props['driveMode'][:] = self.asset_options.default_dof_drive_mode
+        props['stiffness'], props['damping'] = self.cfg.dof_stiffness, self.cfg.dof_damping
+        for column, attr in self._LIMIT_COLUMNS:
+            setattr(self, attr, _tensor(props[column], self.device))
 
     def load_to(self, env_id, env_handle, seg_id):
         super().load_to(env_id, env_handle, seg_id)
@@ -44,49 +41,58 @@ class Robot(Actor):
 
     def init_buffers(self):
         super().init_buffers()
-        n = self.env.num_envs
-        self.default_dof_pos = _t(self.cfg.default_dof_pos, self.device)
-        dof = self.env.dof_state.view(n, self.num_dof, 2)
-        self.dof_pos, self.dof_vel = dof[..., 0], dof[..., 1]
-        self.dof_targets = torch.zeros((n, self.num_dof), dtype=torch.float, device=self.device)
+        envs = self.env.num_envs
+        # (pos, vel) are strided views of the simulator tensor: writes go straight through
+        pos_vel = self.env.dof_state.view(envs, self.num_dof, 2)
+        self.dof_pos, self.dof_vel = pos_vel.select(-1, 0), pos_vel.select(-1, 1)
+        self.default_dof_pos = _tensor(self.cfg.default_dof_pos, self.device)
+        self.dof_targets = torch.zeros(envs, self.num_dof, dtype=torch.float, device=self.device)
+
+    # ---------------------------------------------------------------- actuation
+    def step(self, actions):
+        self._internal_motor_step(actions)
 
     def _internal_motor_step(self, action):
-        mode = self.asset_options.default_dof_drive_mode
-        if mode == gymapi.DOF_MODE_EFFORT:
-            self.gym.set_dof_actuation_force_tensor(self.sim, gymtorch.unwrap_tensor(action))
-        elif mode == gymapi.DOF_MODE_POS:
-            self.gym.set_dof_position_target_tensor(self.sim, gymtorch.unwrap_tensor(action))
-        elif mode == gymapi.DOF_MODE_VEL:
-            self.gym.set_dof_velocity_target_tensor(self.sim, gymtorch.unwrap_tensor(action))
-        else:
-            raise NotImplementedError
+        """Dispatch on the asset's drive mode (robot.py:55-64)."""
+        setters = {gymapi.DOF_MODE_EFFORT: self.gym.set_dof_actuation_force_tensor,
+                   gymapi.DOF_MODE_POS: self.gym.set_dof_position_target_tensor,
+                   gymapi.DOF_MODE_VEL: self.gym.set_dof_velocity_target_tensor}
+        try:
+            setter = setters[self.asset_options.default_dof_drive_mode]
+        except KeyError:
+            raise NotImplementedError from None
+        setter(self.sim, gymtorch.unwrap_tensor(action))
 
     def apply_dof_targets(self, dof_targets):
+        """Position targets held for ``decimation`` simulator substeps (robot.py:66-72)."""
+        wait_for_cpu_sim = self.device == 'cpu'
         for _ in range(int(self.env.decimation)):
             self.gym.set_dof_position_target_tensor(self.sim, gymtorch.unwrap_tensor(dof_targets))
             self.gym.simulate(self.sim)
-            if self.device == 'cpu':
+            if wait_for_cpu_sim:
                 self.gym.fetch_results(self.sim, True)
             self.gym.refresh_dof_state_tensor(self.sim)
 
-    def push_dof_reset(self, env_ids):
-        """Tell the simulator about dof rows that were rewritten in place (robot.py:78-86)."""
-        rows = self.root_indices[env_ids].to(torch.int32)
-        self.gym.set_dof_position_target_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self.dof_targets),
-                                                        gymtorch.unwrap_tensor(rows), len(rows))
-        self.gym.set_dof_state_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self.env.dof_state),
-                                              gymtorch.unwrap_tensor(rows), len(rows))
+    # ---------------------------------------------------------------- reset
+    def reset_idx(self, env_ids):
+        self._reset_dof_state(env_ids)
+        self._reset_root_state(env_ids)
 
     def _reset_dof_state(self, env_ids):
-        self.dof_targets[env_ids] = self.default_dof_pos.clone()
-        self.dof_pos[env_ids] = self.default_dof_pos.clone()
+        rest = self.default_dof_pos
+        self.dof_targets[env_ids] = rest.clone()
+        self.dof_pos[env_ids] = rest.clone()
         self.dof_vel[env_ids] = 0.
         self.push_dof_reset(env_ids)
 
-    @property
-    def base_pose(self):
-        return self.env.root_state[self.root_indices, :7]
+    def push_dof_reset(self, env_ids):
+        """Tell the simulator about dof rows that were rewritten in place (robot.py:78-86)."""
+        rows = gymtorch.unwrap_tensor(self.root_indices[env_ids].to(torch.int32))
+        count = len(env_ids)
+        self.gym.set_dof_position_target_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self.dof_targets), rows, count)
+        self.gym.set_dof_state_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self.env.dof_state), rows, count)
 
+    # ---------------------------------------------------------------- root state
     def get_root_state(self):
         return self.env.root_state[self.root_indices]
 
@@ -103,30 +109,32 @@ class ArmRobot(Robot):
         self.end_effector_names = cfg.end_effector_names
         self.end_effector_velocity = cfg.end_effector_velocity
 
+    def _bind_end_effectors(self):
+        """End-effector body ids, contact view and the jacobian block of the first one (robot.py:117-128)."""
+        bodies = [self.rigid_body_dict[name] for name in self.cfg.end_effector_names]
+        self.ee_indices, self.num_ee = _tensor(bodies, self.device, torch.long), len(bodies)
+        self.contact_forces = self.env.contact_state.view(self.env.num_envs, -1, 3)
+        jacobian = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, self.name))
+        self.gym.refresh_jacobian_tensors(self.sim)
+        return bodies, jacobian
+
     def init_buffers(self):
         super().init_buffers()
-        ee = [self.rigid_body_dict[n] for n in self.cfg.end_effector_names]
-        self.ee_indices = _t(ee, self.device, torch.long)
-        self.num_ee = len(ee)
-        self.contact_forces = self.env.contact_state.view(self.env.num_envs, -1, 3)
-        self.ee_pose_targets = torch.zeros((self.env.num_envs, 7), dtype=torch.float, device=self.device)
-        jac = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, self.name))
-        self.gym.refresh_jacobian_tensors(self.sim)
-        self._jacobian, self._ee_link = jac, ee[0] - 1
-        self.j_ee = jac[:, ee[0] - 1]
+        bodies, jacobian = self._bind_end_effectors()
+        self.ee_pose_targets = torch.zeros(self.env.num_envs, 7, dtype=torch.float, device=self.device)
+        self._jacobian, self._ee_link = jacobian, bodies[0] - 1     # fixed base: link = body - 1
+        self.j_ee = jacobian[:, self._ee_link]
 
     def load_to(self, env_id, env_handle, seg_id):
         super().load_to(env_id, env_handle, seg_id)
         self.set_segmentation_id(env_handle, seg_id)
 
-    def apply_target_end_positions(self, tar_pose):
-        self.dof_targets[:] = self.inverse_kinematics(tar_pose)
-        self.apply_dof_targets(self.dof_targets)
-
+    # ---------------------------------------------------------------- views (robot.py:138-154)
     @property
     def body_state(self):
-        n = self.env.num_envs
-        return self.env.body_state.view(n, -1, 13)[:, :self.num_bodies].view(n, self.num_bodies, -1)
+        envs = self.env.num_envs
+        own = self.env.body_state.view(envs, -1, 13)[:, :self.num_bodies]
+        return own.view(envs, self.num_bodies, -1)
 
     @property
     def ee_pose(self):
@@ -140,25 +148,31 @@ class ArmRobot(Robot):
     def ee_forces(self):
         return self.contact_forces[:, self.ee_indices]
 
+    # ---------------------------------------------------------------- inverse kinematics (row N2)
     @staticmethod
     def orientation_error(desired, current):
         from isaacgym.torch_utils import quat_conjugate, quat_mul
-        q_r = quat_mul(desired, quat_conjugate(current))
-        return q_r[:, 0:3] * torch.sign(q_r[:, 3]).unsqueeze(-1)
+        rel = quat_mul(desired, quat_conjugate(current))
+        return rel[:, :3] * torch.sign(rel[:, 3]).unsqueeze(-1)
 
     def _ik_layout(self):
-        n = self.env.num_envs
-        bodies = self.env.body_state.shape[0] // n
-        if self.env.dof_state.shape[0] // n != self.num_dof:
+        envs = self.env.num_envs
+        if self.env.dof_state.shape[0] // envs != self.num_dof:
             raise NotImplementedError("shifu_arm_ik expects the arm to own every dof of its env")
-        jac = self._jacobian if self._jacobian.is_contiguous() else self._jacobian.contiguous()
-        return dict(body_state=self.env.body_state, num_bodies=bodies, ee_body=int(self.ee_indices[0]),
-                    jacobian=jac, ee_link=self._ee_link, dof_state=self.env.dof_state, num_dof=self.num_dof)
+        jacobian = self._jacobian if self._jacobian.is_contiguous() else self._jacobian.contiguous()
+        return dict(body_state=self.env.body_state, num_bodies=self.env.body_state.shape[0] // envs,
+                    ee_body=int(self.ee_indices[0]), jacobian=jacobian, ee_link=self._ee_link,
+                    dof_state=self.env.dof_state, num_dof=self.num_dof)
 
     def inverse_kinematics(self, goal_pose, damping=0.05, out=None):
         """Damped least squares (robot.py:156-182) — SURVEY.md §8f row N2, one ``shifu_arm_ik`` launch."""
-        out = torch.empty(self.env.num_envs, self.num_dof, device=self.device) if out is None else out
+        if out is None:
+            out = torch.empty(self.env.num_envs, self.num_dof, device=self.device)
         return self.env.kernels().arm_ik(goal_pose=goal_pose, damping=damping, dof_targets=out, **self._ik_layout())
+
+    def apply_target_end_positions(self, tar_pose):
+        self.inverse_kinematics(tar_pose, out=self.dof_targets)
+        self.apply_dof_targets(self.dof_targets)
 
 
 class LeggedRobot(ArmRobot):
@@ -171,23 +185,17 @@ class LeggedRobot(ArmRobot):
 
     def init_buffers(self):
         Robot.init_buffers(self)
-        n, dev = self.env.num_envs, self.device
-        ee = [self.rigid_body_dict[name] for name in self.cfg.end_effector_names]
-        self.ee_indices = _t(ee, dev, torch.long)
-        self.num_ee = len(ee)
-        self.contact_forces = self.env.contact_state.view(n, -1, 3)
-        jac = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, self.name))
-        self.gym.refresh_jacobian_tensors(self.sim)
-        self.j_ee = jac[:, ee]
+        bodies, jacobian = self._bind_end_effectors()
+        self.j_ee = jacobian[:, bodies]
         # body-frame state (robot.py:210-215): persistent tensors updated in place by the kernel
-        self.gravity_vec = torch.tensor([0., 0., -1.], device=dev).repeat(n, 1)
-        self.base_lin_vel = torch.zeros(n, 3, device=dev)
-        self.base_ang_vel = torch.zeros(n, 3, device=dev)
-        self.projected_gravity = torch.zeros(n, 3, device=dev)
+        envs, dev = self.env.num_envs, self.device
+        self.gravity_vec = torch.tensor([0., 0., -1.], device=dev).repeat(envs, 1)
+        self.base_lin_vel, self.base_ang_vel, self.projected_gravity = (torch.zeros(envs, 3, device=dev)
+                                                                        for _ in range(3))
         self.post_step()
 
     def step(self, actions):
-        self.dof_targets[:] = self.dof_pos[:, :self.num_dof] + actions
+        torch.add(self.dof_pos[:, :self.num_dof], actions, out=self.dof_targets)
         self.apply_dof_targets(self.dof_targets)
         self.post_step()
 
@@ -196,11 +204,10 @@ class LeggedRobot(ArmRobot):
         layout = self.affine_root_layout()
         if layout is None:
             raise NotImplementedError("non-affine root_indices are not supported by shifu_body_frame")
-        self.env.kernels().body_frame(self.env.root_state, self.env.num_envs, layout[0], layout[1],
-                                      self.base_lin_vel, self.base_ang_vel, self.projected_gravity,
-                                      self.gravity_vec)
+        stride, offset = layout
+        self.env.kernels().body_frame(self.env.root_state, self.env.num_envs, stride, offset, self.base_lin_vel,
+                                      self.base_ang_vel, self.projected_gravity, self.gravity_vec)
 
     def apply_force_on_base(self, force_tensor, pos_tensor=None):
-        self.gym.apply_rigid_body_force_at_pos_tensors(
-            self.sim, gymtorch.unwrap_tensor(force_tensor),
-            gymtorch.unwrap_tensor(pos_tensor) if pos_tensor is not None else None)
+        positions = None if pos_tensor is None else gymtorch.unwrap_tensor(pos_tensor)
+        self.gym.apply_rigid_body_force_at_pos_tensors(self.sim, gymtorch.unwrap_tensor(force_tensor), positions)

@@ -29,80 +29,93 @@ class CameraPose(enum.Enum):
 class CameraSensor(Sensor):
     cfg: CameraSensorConfig
 
+    # image type -> (key of the gather call, buffer attribute, dtype, channels of the per-env tensor)
+    _SPECS = ((IMAGE_TYPE_COLOR, "color", "color_buf", torch.uint8, 4),
+              (IMAGE_TYPE_DEPTH, "depth", "depth_buf", torch.float32, 0),
+              (IMAGE_TYPE_SEGMENTATION, "seg", "segmentation_buf", torch.int32, 0),
+              (IMAGE_TYPE_OPTICAL_FLOW, "flow", "optical_flow_buf", torch.int16, 0))
+
     def __init__(self, cfg: CameraSensorConfig):
         super().__init__(cfg)
-        self.width = cfg.camera_props.width
-        self.height = cfg.camera_props.height
-        self.near_plane = cfg.camera_props.near_plane
-        self.far_plane = cfg.camera_props.far_plane
+        props = cfg.camera_props
+        self.width, self.height = props.width, props.height
+        self.near_plane, self.far_plane = props.near_plane, props.far_plane
         self._tables = None
 
-    def init_buffers(self):                                    # sensors.py:66-94
-        n, h, w = self.env.num_envs, self.height, self.width
-        for img_type in self.cfg.image_types:
-            if img_type == IMAGE_TYPE_COLOR:
-                self.color_buf = torch.zeros(n, h, w, 3 if self.cfg.image_normalization else 4,
-                                             dtype=torch.float if self.cfg.image_normalization else torch.uint8,
-                                             device=self.device)
-            elif img_type == IMAGE_TYPE_DEPTH:
-                self.depth_buf = torch.zeros(n, h, w, dtype=torch.float, device=self.device)
-            elif img_type == IMAGE_TYPE_SEGMENTATION:
-                self.segmentation_buf = torch.zeros(n, h, w, dtype=torch.int32, device=self.device)
-            elif img_type == IMAGE_TYPE_OPTICAL_FLOW:
-                self.optical_flow_buf = torch.zeros(n, h, w, dtype=torch.int16, device=self.device)
-            else:
+    def init_buffers(self):
+        """Batched buffers (sensors.py:66-94): RGBA u8 or normalised RGB f32, depth f32, segmentation
+        i32, optical flow i16."""
+        known = {spec[0]: spec for spec in self._SPECS}
+        shape = (self.env.num_envs, self.height, self.width)
+        for image_type in self.cfg.image_types:
+            if image_type not in known:
                 raise NotImplementedError
+            _, _, attr, dtype, channels = known[image_type]
+            if image_type == IMAGE_TYPE_COLOR and self.cfg.image_normalization:
+                dtype, channels = torch.float, 3
+            full = shape + ((channels,) if channels else ())
+            setattr(self, attr, torch.zeros(full, dtype=dtype, device=self.device))
 
-    def _init_props(self):                                     # sensors.py:96-115
-        if self.cfg.local_lookat_positions is not None:
-            assert self.cfg.transform is None and self.cfg.attach_local_transform is None
-            self.local_lookat_position = (gymapi.Vec3(*self.cfg.local_lookat_positions[0]),
-                                          gymapi.Vec3(*self.cfg.local_lookat_positions[1]))
-            self._pose_type = CameraPose.LocalLookat
-        elif self.cfg.transform is not None:
-            assert self.cfg.local_lookat_positions is None and self.cfg.attach_local_transform is None
-            self.transform = gymapi.Transform()
-            self.transform.p = gymapi.Vec3(*self.cfg.transform[0])
-            self.transform.r = gymapi.Quat(*self.cfg.transform[1])
-            self._pose_type = CameraPose.Transform
-        elif self.cfg.attach_local_transform is not None:
+    def _init_props(self):
+        """Exactly one way of posing the camera must be configured (sensors.py:96-115)."""
+        cfg = self.cfg
+        if cfg.attach_local_transform is not None and cfg.local_lookat_positions is None and cfg.transform is None:
             raise NotImplementedError('Currently not support')
+        if cfg.local_lookat_positions is not None:
+            assert cfg.transform is None and cfg.attach_local_transform is None
+            eye, target = cfg.local_lookat_positions
+            self.local_lookat_position = (gymapi.Vec3(*eye), gymapi.Vec3(*target))
+            self._pose_type = CameraPose.LocalLookat
+        elif cfg.transform is not None:
+            assert cfg.attach_local_transform is None
+            position, rotation = cfg.transform
+            self.transform = self._make_transform(position, rotation)
+            self._pose_type = CameraPose.Transform
         else:
             raise NotImplementedError('choose one of method from local_lookat_positions and transform')
+
+    @staticmethod
+    def _make_transform(position, rotation):
+        t = gymapi.Transform()
+        t.p, t.r = gymapi.Vec3(*position), gymapi.Quat(*rotation)
+        return t
 
     def reset_idx(self, env_ids):
         pass
 
     def _read_matrices(self, env_handle):
-        self.proj_matrix = np.matrix(self.gym.get_camera_proj_matrix(self.sim, env_handle, self.camera_handle))
-        self.view_matrix = np.matrix(self.gym.get_camera_view_matrix(self.sim, env_handle, self.camera_handle))
+        query = (self.sim, env_handle, self.camera_handle)
+        self.proj_matrix = np.matrix(self.gym.get_camera_proj_matrix(*query))
+        self.view_matrix = np.matrix(self.gym.get_camera_view_matrix(*query))
 
-    def load_to(self, env_id, env_handle, seg_id):             # sensors.py:120-137
-        camera_handle = self.gym.create_camera_sensor(env_handle, self.cfg.camera_props)
-        if self._pose_type == CameraPose.LocalLookat:
+    def _pose(self, camera_handle, env_handle):
+        if self._pose_type is CameraPose.LocalLookat:
             self.gym.set_camera_location(camera_handle, env_handle, *self.local_lookat_position)
-        elif self._pose_type == CameraPose.Transform:
+        elif self._pose_type is CameraPose.Transform:
             self.gym.set_camera_transform(camera_handle, env_handle, self.transform)
         else:
             raise NotImplementedError
-        if env_id == 0:
-            self.camera_handle = camera_handle
+
+    def load_to(self, env_id, env_handle, seg_id):             # sensors.py:120-137
+        handle = self.gym.create_camera_sensor(env_handle, self.cfg.camera_props)
+        self._pose(handle, env_handle)
+        if env_id == 0:                                        # all envs share handle and intrinsics
+            self.camera_handle = handle
             self._read_matrices(env_handle)
 
     def set_camera_transform(self, position, rotation):        # sensors.py:139-148
+        """Re-pose every env's camera.  Reference quirk kept: env 0 is given the transform that was
+        current before the call, the new one takes effect from env 1 on."""
         for env_id, env_handle in enumerate(self.env.env_handles):
-            transform = gymapi.Transform()
-            transform.p = gymapi.Vec3(*position)
-            transform.r = gymapi.Quat(*rotation)
             self.gym.set_camera_transform(self.camera_handle, env_handle, self.transform)
             if env_id == 0:
-                self.transform = transform
+                self.transform = self._make_transform(position, rotation)
                 self._read_matrices(env_handle)
 
     def set_camera_location(self, local_pos, lookat_pos):      # sensors.py:150-159
+        eye, target = gymapi.Vec3(*local_pos), gymapi.Vec3(*lookat_pos)
         for env_id, env_handle in enumerate(self.env.env_handles):
-            self.gym.set_camera_location(self.camera_handle, env_handle, gymapi.Vec3(*local_pos),
-                                         gymapi.Vec3(*lookat_pos))
+            self.gym.set_camera_location(self.camera_handle, env_handle, eye, target)
             if env_id == 0:
                 self.local_lookat_position = (local_pos, lookat_pos)
                 self._read_matrices(env_handle)
@@ -111,10 +124,6 @@ class CameraSensor(Sensor):
         self.refresh_image_tensors()
 
     # -- the batched gather ---------------------------------------------------------------------
-    _SPECS = ((IMAGE_TYPE_COLOR, "color", "color_buf", torch.uint8, 4),
-              (IMAGE_TYPE_DEPTH, "depth", "depth_buf", torch.float32, 0),
-              (IMAGE_TYPE_SEGMENTATION, "seg", "segmentation_buf", torch.int32, 0),
-              (IMAGE_TYPE_OPTICAL_FLOW, "flow", "optical_flow_buf", torch.int16, 0))
 
     def _build_tables(self):
         """One pass over the envs (at the first refresh, not per step): the interop tensors Isaac Gym
