@@ -139,3 +139,25 @@ def test_torch_philox_matches_oracle_philox():
     assert np.array_equal(u, px.u01_f32(px.draw_u32(0x5EED, ids.numpy(), 3, 1)[:2]).T)
     r = philox.draw_randint(0x5EED, ids, 3, 0, 10).numpy()
     assert np.array_equal(r, px.randint10(px.draw_u32(0x5EED, ids.numpy(), 3, 0)[0], 10))
+
+
+def test_build_is_keyed_on_source_content_not_mtimes(tmp_path, monkeypatch):
+    """One process per GPU shares the tree: a touched-but-unchanged source (git checkout, a
+    snapshot copy) must not make every rank rebuild the library; a changed source must."""
+    import shutil
+    from shifu_b200 import build as b
+    assert not b.needs_build()
+    pkg = tmp_path / "shifu_b200"
+    shutil.copytree(b.PKG_DIR, pkg, ignore=shutil.ignore_patterns("__pycache__", "*.tmp*"))
+    shutil.copytree(b.INCLUDE, tmp_path / "include")
+    monkeypatch.setattr(b, "PKG_DIR", str(pkg))
+    monkeypatch.setattr(b, "CSRC", str(pkg / "csrc"))
+    monkeypatch.setattr(b, "INCLUDE", str(tmp_path / "include"))
+    monkeypatch.setattr(b, "LIB_PATH", str(pkg / "libshifu_b200.so"))
+    monkeypatch.setattr(b, "STAMP_PATH", str(pkg / "libshifu_b200.so.srchash"))
+    assert not b.needs_build()                        # relocated copy: same content, same stamp
+    src = pkg / "csrc" / "philox.cuh"
+    os.utime(src)                                     # newer mtime, same bytes
+    assert not b.needs_build()
+    src.write_text(src.read_text() + "\n// changed\n")
+    assert b.needs_build()
