@@ -302,8 +302,7 @@ a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ Sh
         const unsigned py = min(__float2uint_rz(fy), max_py);
         int idx;
         if (TILED) {
-          const unsigned tile = (px >> TILE_SHIFT) * (unsigned)k.tiles_y + (py >> TILE_SHIFT);
-          idx = (int)((tile << (2 * TILE_SHIFT)) | ((px & 7u) << TILE_SHIFT) | (py & 7u));
+          idx = (int)((px & ~7u) * (unsigned)(k.band_w - 1) + px + (py << TILE_SHIFT));
         } else {
           idx = (int)(px * (unsigned)k.tcols + py);
         }

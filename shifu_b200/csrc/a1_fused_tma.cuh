@@ -105,6 +105,36 @@ __device__ unsigned long long v3_prof[32];
 #define V3_COUNT(slot)
 #endif
 
+// dev knobs for the cache behaviour of the table gathers and the obs stores
+#ifndef V3_LD_MODE
+#define V3_LD_MODE 0
+#endif
+#ifndef V3_ST_MODE
+#define V3_ST_MODE 0
+#endif
+__device__ __forceinline__ int v3_gather(const short* p) {
+#if V3_LD_MODE == 0
+  return __ldg(p);
+#elif V3_LD_MODE == 1
+  short v; asm volatile("ld.global.s16 %0, [%1];" : "=h"(v) : "l"(p)); return v;
+#elif V3_LD_MODE == 2
+  short v; asm volatile("ld.global.nc.L1::evict_last.s16 %0, [%1];" : "=h"(v) : "l"(p)); return v;
+#else
+  short v; asm volatile("ld.global.L1::evict_last.s16 %0, [%1];" : "=h"(v) : "l"(p)); return v;
+#endif
+}
+__device__ __forceinline__ void v3_store(float* p, float v) {
+#if V3_ST_MODE == 0
+  __stcs(p, v);
+#elif V3_ST_MODE == 1
+  *p = v;
+#elif V3_ST_MODE == 2
+  __stcg(p, v);
+#else
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+#endif
+}
+
 constexpr uint32_t V3_ROW_BYTES = offsetof(V3In, ep_len);
 constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
 
@@ -196,12 +226,19 @@ __global__ void __launch_bounds__(V3_THREADS, V3_CTAS_PER_SM)
 a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V3Smem& s = *reinterpret_cast<V3Smem*>(smem_raw);
+#ifdef V3_SCAN_FIRST
+  // warp order scan | B | DMA: the hardware arbiter favours high warp ids, which puts the
+  // latency-critical B group ahead of the throughput-bound scan warps
+  const int t = (threadIdx.x < V3_C_THREADS) ? (int)threadIdx.x + V3_B_THREADS
+              : ((threadIdx.x < V3_C_THREADS + V3_B_THREADS) ? (int)threadIdx.x - V3_C_THREADS : (int)threadIdx.x);
+#else
   const int t = threadIdx.x;
+#endif
   const long long step = (io.step_dev != nullptr) ? *io.step_dev : io.step;
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_tiles = (first < num_tiles) ? (num_tiles - first + stride - 1) / stride : 0;
 
-  if (t == 0) {
+  if (threadIdx.x == 0) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       pipe::mbar_init(&s.full_in[b], 1);
@@ -267,7 +304,11 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       bool contact_term = false;
 #pragma unroll 1
       for (int q = warp; q < k.n_terms; q += 2)
+#ifdef V3_WI_NOB1
+        s.rterm[g][q][lane] = 0.0f;
+#else
         s.rterm[g][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane);
+#endif
       if (warp == 0) {                                                    // a1_conditional.py:146-148
         const float* fb = &in.contact[lane][k.base_body * 3];
         contact_term = fma_rn(fb[2], fb[2], fma_rn(fb[1], fb[1], mul_rn(fb[0], fb[0]))) > k.contact_thr_sq;
@@ -340,13 +381,15 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     const float bx = k.px[p % A1_NX], by = k.py[(p / A1_NX) % A1_NY];
     const float hclip = fminf(k.h_clip, k.clip_obs);         // clip(clip(v,+-a),+-b) == clip(v,+-min(a,b))
     const unsigned max_px = (unsigned)(k.trows - 1), max_py = (unsigned)(k.tcols - 1);
-    // tiled index: ((px>>3)*tiles_y + (py>>3))*64 + (px&7)*8 + (py&7)
-    //            == (px & ~7)*8*(tiles_y-1) + 8*px  +  (py & ~7)*7 + py          (5 integer ops)
-    const unsigned c1 = 8u * (unsigned)(k.tiles_y - 1);
+    // banded index: (px>>3)*8*W + py*8 + (px&7)  ==  (px & ~7)*(W-1) + px + 8*py    (3 integer ops)
+    const unsigned c1 = (unsigned)(k.band_w - 1);
     const short* __restrict__ table = k.table;
     const f2_t BX = pk(bx, bx), BY = pk(by, by), NBY = pk(-by, -by), BORDER = pk(k.border, k.border);
     const f2_t RCP = pk(k.hdiv.r, k.hdiv.r), NEGD = pk(-k.hdiv.d, -k.hdiv.d), VS = pk(k.vscale, k.vscale);
     const f2_t NZ = pk(k.neg_zero, k.neg_zero);
+#ifndef V3_F2I_CVT
+    const f2_t DENORM = pk(__int_as_float(1), __int_as_float(1));     // 2^-149
+#endif
     V3_T0(p == 0);
     for (int j = 0; j < my_tiles; ++j) {
       const int b = j & 1;
@@ -363,13 +406,15 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           const int e = i / A1_DOF, d = i - e * A1_DOF;
           float* h = io.obs_buf + (e0 + e) * A1_OBS;
           const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
-          __stcs(h + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
-          __stcs(h + 24 + d, clampf(qd.y, -c, c));
           const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
                       a2 = in.hist[e][d * A1_HIST + 2];
+#ifndef V3_WI_NOHEAD
+          __stcs(h + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
+          __stcs(h + 24 + d, clampf(qd.y, -c, c));
           __stcs(h + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
           __stcs(h + 48 + d, clampf(a1, -c, c));
           __stcs(h + 60 + d, clampf(a2, -c, c));
+#endif
           in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
           in.hist[e][d * A1_HIST + 1] = a0;
           in.hist[e][d * A1_HIST + 0] = in.act[e][d];
@@ -377,9 +422,14 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
           const int e = i / 12, q = i - e * 12;
           const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
+#ifndef V3_WI_NOHEAD
           __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
+#endif
         }
-        // carried body-frame velocities for the next control step (robot.py:222-229, D7)
+        // carried body-frame velocities for the next control step (robot.py:222-229, D7): one
+        // rotation per (env, vector) item on half of the scan warps, the halves alternating from tile
+        // to tile so that no warp is permanently the slowest of the group
+#ifdef V3_CARRY_ONE_WARP
         if (io.carry_body_frame && p >= V3_C_THREADS - 32) {
           const int e = p - (V3_C_THREADS - 32);
           const long long ge = e0 + e;
@@ -393,19 +443,37 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           io.projected_gravity[ge * 3 + 0] = o[0]; io.projected_gravity[ge * 3 + 1] = o[1];
           io.projected_gravity[ge * 3 + 2] = o[2];
         }
+#else
+        if (io.carry_body_frame) {
+          const int it = p - ((j & 1) ? 96 : 0);                 // item = (vector, env): 3 x 32
+          if (it >= 0 && it < 96) {
+            const int v = it >> 5, e = it & 31;
+            const long long ge = e0 + e;
+            const float* r = in.root[e];
+            float o[3];
+            rotate_inverse(r + 3, v == 2 ? 0.0f : r[7 + 3 * v], v == 2 ? 0.0f : r[8 + 3 * v],
+                           v == 2 ? -1.0f : r[9 + 3 * v], o);
+            float* dst = (v == 0 ? io.base_lin_vel : (v == 1 ? io.base_ang_vel : io.projected_gravity)) + ge * 3;
+            dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+          }
+        }
+#endif
       }
       pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
       pipe::mbar_arrive(&s.h_done[b]);
       V3_TICK(9);
+#ifdef V3_WI_NOSCAN
+      if (p < 0) {
+#else
       if (p < A1_POINTS) {
+#endif
         float* ob = io.obs_buf + e0 * A1_OBS + A1_HEAD + p;
         float* mb = HAS_MROW ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
         // Batches of 8 envs (4 pairs): index arithmetic in packed fp32x2 (two envs per
         // instruction), then the 8 table gathers back to back.  The four batches of a tile are
         // software-pipelined in registers: batch i+1's arithmetic and gathers are issued before
         // batch i's gathered heights are consumed, so the gather latency overlaps arithmetic.
-        auto gather_batch = [&](int q0, int (&h)[8]) {
-          unsigned idx[8];
+        auto index_batch = [&](int q0, unsigned (&idx)[8]) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float4 a = s.sA[rb][q0 + u], bq = s.sB[rb][q0 + u];
@@ -423,25 +491,46 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             const f2_t ry = add2(add2(BY, fma2(W, ty, NZ)), fma2(Z, tx, NZ));
             // + base xy, + border, / horizontal_scale (isaac_gym.py:416-421)
             const f2_t ax = add2(add2(rx, X), BORDER), ay = add2(add2(ry, Y), BORDER);
-            float fx0, fx1, fy0, fy1;
+            unsigned px0, px1, py0, py1;
             if (EXACT_DIV) {
               float a0, a1, b0, b1;
               upk(ax, a0, a1); upk(ay, b0, b1);
-              fx0 = div_rn(a0, k.hdiv.d); fx1 = div_rn(a1, k.hdiv.d);
-              fy0 = div_rn(b0, k.hdiv.d); fy1 = div_rn(b1, k.hdiv.d);
+              // .long() + clip (isaac_gym.py:421-425): float->uint truncates and saturates at 0
+              px0 = min(__float2uint_rz(div_rn(a0, k.hdiv.d)), max_px);
+              px1 = min(__float2uint_rz(div_rn(a1, k.hdiv.d)), max_px);
+              py0 = min(__float2uint_rz(div_rn(b0, k.hdiv.d)), max_py);
+              py1 = min(__float2uint_rz(div_rn(b1, k.hdiv.d)), max_py);
             } else {                         // q0 = x*r; e = fma(-d, q0, x); q = fma(e, r, q0)
               const f2_t qx = mul2(ax, RCP), qy = mul2(ay, RCP);
-              upk(fma2(fma2(NEGD, qx, ax), RCP, qx), fx0, fx1);
-              upk(fma2(fma2(NEGD, qy, ay), RCP, qy), fy0, fy1);
+              const f2_t fx = fma2(fma2(NEGD, qx, ax), RCP, qx), fy = fma2(fma2(NEGD, qy, ay), RCP, qy);
+#ifndef V3_F2I_CVT
+              // .long() + clip without the conversion unit: RZ(f * 2^-149) is the denormal whose bit
+              // pattern IS trunc(f) for 0 <= f < 2^23 (negative f -> sign bit -> relu -> 0, larger f
+              // -> a normal number >= 2^23 -> upper clip); one packed multiply per env pair
+              int ix0, ix1, iy0, iy1;
+              upk_i(mulrz2(fx, DENORM), ix0, ix1);
+              upk_i(mulrz2(fy, DENORM), iy0, iy1);
+              px0 = (unsigned)__vimin_s32_relu(ix0, (int)max_px); px1 = (unsigned)__vimin_s32_relu(ix1, (int)max_px);
+              py0 = (unsigned)__vimin_s32_relu(iy0, (int)max_py); py1 = (unsigned)__vimin_s32_relu(iy1, (int)max_py);
+#else
+              float fx0, fx1, fy0, fy1;
+              upk(fx, fx0, fx1); upk(fy, fy0, fy1);
+              px0 = min(__float2uint_rz(fx0), max_px); px1 = min(__float2uint_rz(fx1), max_px);
+              py0 = min(__float2uint_rz(fy0), max_py); py1 = min(__float2uint_rz(fy1), max_py);
+#endif
             }
-            // .long() + clip (isaac_gym.py:421-425): float->uint truncates and saturates at 0
-            const unsigned px0 = min(__float2uint_rz(fx0), max_px), px1 = min(__float2uint_rz(fx1), max_px);
-            const unsigned py0 = min(__float2uint_rz(fy0), max_py), py1 = min(__float2uint_rz(fy1), max_py);
-            idx[2 * u] = (px0 & ~7u) * c1 + ((py0 & ~7u) * 7u + py0) + (px0 << 3);
-            idx[2 * u + 1] = (px1 & ~7u) * c1 + ((py1 & ~7u) * 7u + py1) + (px1 << 3);
+            idx[2 * u] = ((px0 & ~7u) * c1 + px0) + (py0 << 3);
+            idx[2 * u + 1] = ((px1 & ~7u) * c1 + px1) + (py1 << 3);
           }
+        };
+        auto load_batch = [&](const unsigned (&idx)[8], int (&h)[8]) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) h[u] = __ldg(table + idx[u]);          // isaac_gym.py:427-431 (folded)
+          for (int u = 0; u < 8; ++u) h[u] = v3_gather(table + idx[u]);      // isaac_gym.py:427-431 (folded)
+        };
+        auto gather_batch = [&](int q0, int (&h)[8]) {
+          unsigned idx[8];
+          index_batch(q0, idx);
+          load_batch(idx, h);
         };
         auto store_batch = [&](int q0, const int (&h)[8]) {
 #pragma unroll
@@ -450,8 +539,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             const f2_t hg = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
             float v0, v1;
             upk(sub2(pk(zb.x, zb.y), hg), v0, v1);                            // (z - 0.5) - h, a1_conditional.py:132
-            __stcs(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
-            __stcs(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
+            v3_store(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
+            v3_store(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
             if (HAS_MROW) {
               float g0, g1;
               upk(hg, g0, g1);
@@ -462,14 +551,14 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           ob += 8 * A1_OBS;
           if (HAS_MROW) mb += 8 * A1_POINTS;
         };
-#ifdef V3_NO_PIPE_SCAN
+#if defined(V3_NO_PIPE_SCAN)
 #pragma unroll 1
         for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
           int h[8];
           gather_batch(q0, h);
           store_batch(q0, h);
         }
-#else
+#elif defined(V3_MOVE_PIPE)
         // rolled on purpose: the loop body (one gather_batch + one store_batch) stays small enough
         // for the instruction cache shared with the other warp roles
         int hc[8];   // sign-extended int16 cells: plain register moves below, no 16-bit packing
@@ -482,6 +571,22 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 8; ++u) hc[u] = hn[u];
         }
+#else
+        // Rolled software pipeline (the body stays small enough for the instruction cache shared with
+        // the other warp roles): the gathers of batch i are issued at the END of a trip and consumed
+        // in the MIDDLE of the next one, after the index arithmetic of batch i+1 — so their L1/L2
+        // latency hides under ~200 instructions of independent math, with no register copies.
+        unsigned idx[8];
+        int h[8];    // sign-extended int16 cells
+        index_batch(0, idx);
+        load_batch(idx, h);
+#pragma unroll 1
+        for (int q0 = 0; q0 < A1_TILE / 2 - 4; q0 += 4) {
+          index_batch(q0 + 4, idx);
+          store_batch(q0, h);
+          load_batch(idx, h);
+        }
+        store_batch(A1_TILE / 2 - 4, h);
 #endif
       }
       V3_TICK(17);

@@ -17,7 +17,7 @@ constexpr int A1_NX = 17, A1_NY = 11, A1_POINTS = A1_NX * A1_NY;   // 187
 constexpr int A1_HEAD = A1_OBS - A1_POINTS;                          // 72 non-height obs columns
 constexpr int A1_TILE = 32;       // envs per CTA
 constexpr int A1_THREADS = 192;   // 6 warps: 187 scan points + 5 idle lanes
-constexpr int TILE_SHIFT = 3;     // scan table stored in 8x8-cell tiles (128 B each)
+constexpr int TILE_SHIFT = 3;     // scan table stored in bands of 8 map rows: a 128-B line = 8x8 cells
 
 // Kernel-side constants (passed by value as a __grid_constant__ parameter: constant bank).
 struct A1K {
@@ -49,8 +49,8 @@ struct A1K {
   // scan table
   const short* table;     // tiled min-of-3 table
   int trows, tcols;       // valid index range: px in [0, trows-1], py in [0, tcols-1]
-  int tiles_y;            // tiles per table row
-  int tiled;              // 1: 8x8 tiles, 0: row-major (pitch = tcols)
+  int band_w;             // banded layout: entries per map row inside a band (tcols padded to 8)
+  int tiled;              // 1: banded (T[px>>3][py][px&7], a 128-B line = 8x8 cells), 0: row-major (pitch = tcols)
   double* stats;          // SHIFU_NUM_STATS accumulators
   float neg_zero;         // -0.0f, opaque to ptxas: see mulx2() in a1_fused_tma.cuh
 };
@@ -60,10 +60,8 @@ __device__ __forceinline__ float hdivide(float x, const A1K& k) {
 }
 
 __device__ __forceinline__ int table_index(unsigned px, unsigned py, const A1K& k) {
-  if (k.tiled) {
-    const unsigned tile = (px >> TILE_SHIFT) * (unsigned)k.tiles_y + (py >> TILE_SHIFT);
-    return (int)((tile << (2 * TILE_SHIFT)) | ((px & 7u) << TILE_SHIFT) | (py & 7u));
-  }
+  if (k.tiled)     // (px>>3)*8*W + py*8 + (px&7)  ==  (px & ~7)*(W-1) + px + 8*py      (3 integer ops)
+    return (int)((px & ~7u) * (unsigned)(k.band_w - 1) + px + (py << TILE_SHIFT));
   return (int)(px * (unsigned)k.tcols + py);
 }
 
@@ -72,7 +70,7 @@ __device__ __forceinline__ int table_index(unsigned px, unsigned py, const A1K& 
 // (shifu/gym/isaac_gym.py:427-431 folded; the map is static after create_ground()).
 // ------------------------------------------------------------------------------------------
 __global__ void build_scan_table_kernel(const short* __restrict__ H, int rows, int cols,
-                                        short* __restrict__ T, int tiles_y, int tiled) {
+                                        short* __restrict__ T, int band_w, int tiled) {
   const int trows = rows - 1, tcols = cols - 1;
   const long long total = (long long)trows * tcols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -84,8 +82,7 @@ __global__ void build_scan_table_kernel(const short* __restrict__ H, int rows, i
     const short m = min(min(a, b), c);
     long long o;
     if (tiled) {
-      const long long tile = (long long)(px >> TILE_SHIFT) * tiles_y + (py >> TILE_SHIFT);
-      o = (tile << (2 * TILE_SHIFT)) | ((px & 7) << TILE_SHIFT) | (py & 7);
+      o = (long long)(px >> TILE_SHIFT) * 8 * band_w + (long long)py * 8 + (px & 7);
     } else {
       o = (long long)px * tcols + py;
     }

@@ -71,6 +71,9 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" const char* shifu_last_error(void) { return g_err; }
 extern "C" int shifu_abi_version(void) { return SHIFU_ABI_VERSION; }
 
+#ifdef V3_DEV
+#include "dev_scan_only.cuh"
+#endif
 #ifdef V3_PROFILE
 // dev-only (tools/prof_phases.py): read and optionally clear the fused kernel's phase timers
 extern "C" int shifu_debug_profile(unsigned long long* out, int reset) {
@@ -310,18 +313,20 @@ extern "C" int shifu_set_height_map(ShifuCtx* c, const int16_t* hs, int32_t rows
   const char* layout = getenv("SHIFU_TABLE_LAYOUT");
   const int tiled = (layout != nullptr && strcmp(layout, "rowmajor") == 0) ? 0 : 1;
   const int trows = rows - 1, tcols = cols - 1;
-  const int tiles_x = (trows + 7) / 8, tiles_y = (tcols + 7) / 8;
-  const size_t elems = tiled ? (size_t)tiles_x * tiles_y * 64 : (size_t)trows * tcols;
+  // banded layout T[px>>3][py][px&7]: the 8 rows of a band are interleaved per column, so a 128-B
+  // line still holds an 8x8-cell patch of the map while the index needs 3 integer ops
+  const int bands = (trows + 7) / 8, band_w = ((tcols + 7) / 8) * 8;
+  const size_t elems = tiled ? (size_t)bands * 8 * band_w : (size_t)trows * tcols;
   CUDA_TRY(cudaStreamSynchronize(S(stream)));
   if (c->d_table != nullptr) { cudaFree(c->d_table); c->d_table = nullptr; }
   CUDA_TRY(cudaMalloc(&c->d_table, elems * sizeof(short)));
   CUDA_TRY(cudaMemsetAsync(c->d_table, 0, elems * sizeof(short), S(stream)));
   build_scan_table_kernel<<<grid_for((long long)trows * tcols, 256, c->sm_count, 8), 256, 0, S(stream)>>>(
-      hs, rows, cols, c->d_table, tiles_y, tiled);
+      hs, rows, cols, c->d_table, band_w, tiled);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(S(stream)));
   c->a1k.table = c->d_table;
-  c->a1k.trows = trows; c->a1k.tcols = tcols; c->a1k.tiles_y = tiles_y; c->a1k.tiled = tiled;
+  c->a1k.trows = trows; c->a1k.tcols = tcols; c->a1k.band_w = band_w; c->a1k.tiled = tiled;
   return SHIFU_OK;
 }
 
@@ -368,6 +373,22 @@ extern "C" int shifu_get_heights(ShifuCtx* c, const float* root, float* mh, int3
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }
+
+#ifdef V3_DEV
+extern "C" int shifu_debug_scan_only(ShifuCtx* c, const float* root, float* obs, int mode, int ctas_per_sm, int threads,
+                                     void* stream) {
+  const int tiles = c->a1.num_envs / A1_TILE;
+  const int grid = c->sm_count * ctas_per_sm;
+  const int np = (mode >> 8) & 15;      // pairs per batch: 2, 4 or 8
+  mode &= 255;
+#define DEV_LAUNCH(T, P) dev_scan_only_kernel<T, P><<<grid, T, 0, S(stream)>>>(c->a1k, root, obs, tiles, mode)
+  if (threads == 192) { if (np == 8) DEV_LAUNCH(192, 8); else if (np == 2) DEV_LAUNCH(192, 2); else DEV_LAUNCH(192, 4); }
+  else if (threads == 384) { if (np == 8) DEV_LAUNCH(384, 8); else if (np == 2) DEV_LAUNCH(384, 2); else DEV_LAUNCH(384, 4); }
+  else { if (np == 8) DEV_LAUNCH(768, 8); else DEV_LAUNCH(768, 4); }
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+#endif
 
 extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void* stream) {
   REQUIRE_PTR(c); REQUIRE_PTR(io);

@@ -32,6 +32,15 @@ __device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// round-toward-zero product, denormal results kept (no .ftz)
+__device__ __forceinline__ f2_t mulrz2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void upk_i(f2_t v, int& lo, int& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
 __device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
   f2_t r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
