@@ -261,6 +261,13 @@ int shifu_a1_post_physics(ShifuCtx* ctx, const ShifuA1StepIO* io, void* stream);
 int shifu_a1_reset_idx(ShifuCtx* ctx, const ShifuA1StepIO* io, const int64_t* env_ids, int32_t n_ids,
                        void* stream);
 
+/* ---- row a16 stand-alone: ShifuVecEnv.reset_idx(env_ids) of the ABB push-box scene -----------
+ * (env.py:114-130 with RandPosBox._reset_root_state, a_prior_stage.py:39-51; used by
+ * ShifuVecEnv.reset, env.py:108-112).  env_ids: device int64 (n_ids), NULL = arange(n_ids).
+ * Adds the episode sums / success flags of the ids to the statistics accumulators. */
+int shifu_abb_reset_idx(ShifuCtx* ctx, const ShifuAbbStepIO* io, const int64_t* env_ids, int32_t n_ids,
+                        void* stream);
+
 /* ---- row a16 -------------------------------------------------------------------------------- */
 int shifu_abb_post_physics(ShifuCtx* ctx, const ShifuAbbStepIO* io, void* stream);
 
@@ -344,6 +351,13 @@ int shifu_collect_stats(ShifuCtx* ctx, double* stats_out, int64_t* step_dev_to_a
  * extras_out: float[SHIFU_NUM_STATS] persistent device array:
  *   [k] term k mean, [8] n_reset (as float), [9] terrain_levels mean, [10] success_rate. */
 int shifu_publish_extras(ShifuCtx* ctx, const double* stats, float* extras_out, void* stream);
+/* Same, into slot `slot` of a ring of `slots` such arrays (float[slots][SHIFU_NUM_STATS]): every step
+ * gets its own array, so the extras dicts of earlier steps that a caller still holds (rsl_rl keeps one
+ * per rollout step; the reference allocates fresh tensors on every resetting step, env.py:124-130)
+ * are not overwritten; a step without resets copies the previous slot.  slot < 0: the slot is
+ * (*step_dev - 1) % slots, for graph-replayed steps whose counter lives on the device. */
+int shifu_publish_extras_ring(ShifuCtx* ctx, const double* stats, float* ring, int32_t slots, int32_t slot,
+                              const int64_t* step_dev, void* stream);
 
 /* Synchronising convenience for tests: copy the accumulator as it stands to the host. */
 int shifu_read_stats_host(ShifuCtx* ctx, double* stats_host, void* stream);

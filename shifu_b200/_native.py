@@ -135,8 +135,10 @@ SIGNATURES = {
     "shifu_arm_ik": [_VP, C.POINTER(ArmIkIO), _I32, _VP],
     "shifu_camera_gather": [_VP, C.POINTER(CameraGatherIO), _I32, _VP],
     "shifu_a1_reset_idx": [_VP, C.POINTER(A1StepIO), _VP, _I32, _VP],
+    "shifu_abb_reset_idx": [_VP, C.POINTER(AbbStepIO), _VP, _I32, _VP],
     "shifu_collect_stats": [_VP, _VP, _VP, _VP],
     "shifu_publish_extras": [_VP, _VP, _VP, _VP],
+    "shifu_publish_extras_ring": [_VP, _VP, _VP, _I32, _I32, _VP, _VP],
     "shifu_read_stats_host": [_VP, _VP, _VP],
 }
 _RESTYPES = {"shifu_last_error": C.c_char_p}

@@ -32,8 +32,15 @@ namespace shifu {
 #ifndef V3_B_GROUPS_CFG
 #define V3_B_GROUPS_CFG 1
 #endif
+#ifndef V3_SCAN_WARPS
+#define V3_SCAN_WARPS 12
+#endif
 #ifndef V3_CTAS_CFG
+#if V3_SCAN_WARPS == 6
 #define V3_CTAS_CFG 3
+#else
+#define V3_CTAS_CFG 2
+#endif
 #endif
 #ifndef V3_POLL_B
 #define V3_POLL_B 64
@@ -49,10 +56,23 @@ namespace shifu {
 #else
 #define V3_WAIT(ns, bar, par) pipe::mbar_wait<ns>(bar, par)
 #endif
-constexpr int V3_B_GROUPS = V3_B_GROUPS_CFG;   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
+#ifndef V3_STAGES_CFG
+#if V3_SCAN_WARPS == 12
+#define V3_STAGES_CFG 3
+#else
+#define V3_STAGES_CFG 2
+#endif
+#endif
+constexpr int V3_STAGES = V3_STAGES_CFG;          // input stages per CTA (the scalar ring holds 4)
+constexpr int V3_B_GROUPS = V3_B_GROUPS_CFG;
+static_assert(V3_B_GROUPS == 1, "one B group per CTA (the stage ring assumes it)");   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
 constexpr int V3_CTAS_PER_SM = V3_CTAS_CFG;
-constexpr int V3_BG_THREADS = 64, V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 192, V3_DMA_THREADS = 32;
-constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;   // 352
+constexpr int V3_BG_THREADS = 64, V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 32 * V3_SCAN_WARPS;
+constexpr int V3_DMA_THREADS = 32;
+constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;
+constexpr int V3_SCAN_BASE = V3_B_THREADS;
+constexpr int V3_DMA_BASE = V3_B_THREADS + V3_C_THREADS;
+static_assert(V3_SCAN_WARPS == 6 || V3_SCAN_WARPS == 12, "scan group: 6 or 12 warps");
 
 struct alignas(128) V3In {            // one tile of simulator/env rows, each member 16-B aligned
   float root[A1_TILE][13];            //  1664 B
@@ -69,10 +89,11 @@ struct alignas(128) V3In {            // one tile of simulator/env rows, each me
   long long level[A1_TILE];           //   256 B  terrain_levels        } (curriculum only)
   long long ttype[A1_TILE];           //   256 B  terrain_types         }
 };
+static_assert(V3_STAGES >= 2 && V3_STAGES <= 4, "ring depth");
 static_assert(sizeof(V3In) == 22272 && offsetof(V3In, ep_len) == 18944, "tile layout");
 
 struct alignas(128) V3Smem {
-  V3In in[2];
+  V3In in[V3_STAGES];
   // per-env scan scalars, laid out per env PAIR (e, e+1) so that one 128-bit broadcast load yields
   // two packed fp32x2 operands: sA = (2zq_e, 2zq_e1, zq_e, zq_e1), sB = (wq_e, wq_e1, x_e, x_e1),
   // sC = (y_e, y_e1, zb_e, zb_e1); (zq, wq) = normalised yaw quaternion of the PRE-reset pose,
@@ -81,10 +102,12 @@ struct alignas(128) V3Smem {
   float4 sA[4][A1_TILE / 2];
   float4 sB[4][A1_TILE / 2];
   float4 sC[4][A1_TILE / 2];
-  float rterm[V3_B_GROUPS][SHIFU_MAX_REWARD_TERMS][A1_TILE];
-  uint64_t full_in[2], b_done[2], h_done[2];
+  // double-buffered on the tile parity: warp 1 may start the next tile's terms while warp 0 still
+  // accumulates this tile's
+  float rterm[2][SHIFU_MAX_REWARD_TERMS][A1_TILE];
+  uint64_t full_in[V3_STAGES], e_done[V3_STAGES], b_done[V3_STAGES], h_done[V3_STAGES];
 #ifdef V3_PROFILE
-  long long t_issue[2];
+  long long t_issue[V3_STAGES];
 #endif
 };
 
@@ -113,6 +136,9 @@ __device__ unsigned long long v3_prof[32];
 #define V3_ST_MODE 0
 #endif
 __device__ __forceinline__ int v3_gather(const short* p) {
+#ifdef V3_WI_NOGATHER
+  return (int)((unsigned long long)p & 1023);     // what-if: no table access
+#endif
 #if V3_LD_MODE == 0
   return __ldg(p);
 #elif V3_LD_MODE == 1
@@ -124,6 +150,10 @@ __device__ __forceinline__ int v3_gather(const short* p) {
 #endif
 }
 __device__ __forceinline__ void v3_store(float* p, float v) {
+#ifdef V3_WI_NOSTORE
+  if (v == 123.456f) *p = v;      // what-if: keep the value alive, (almost) never store
+  return;
+#endif
 #if V3_ST_MODE == 0
   __stcs(p, v);
 #elif V3_ST_MODE == 1
@@ -135,6 +165,11 @@ __device__ __forceinline__ void v3_store(float* p, float v) {
 #endif
 }
 
+// what-if: spin for N cycles (dev builds only) to find out which role is on the critical path
+__device__ __forceinline__ void v3_delay(int cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) { }
+}
 constexpr uint32_t V3_ROW_BYTES = offsetof(V3In, ep_len);
 constexpr uint32_t V3_HIST_BYTES = A1_TILE * A1_DOF * A1_HIST * 4;
 
@@ -144,7 +179,12 @@ __device__ __forceinline__ void v3_issue_hist_load(V3In& in, const ShifuA1StepIO
   pipe::bulk_load(in.hist, io.history + e0 * (A1_DOF * A1_HIST), sizeof(in.hist), bar);
 }
 
-__device__ __noinline__ void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
+#if V3_SCAN_WARPS == 12 || defined(V3_INLINE)
+#define V3_NOINLINE __forceinline__
+#else
+#define V3_NOINLINE __noinline__
+#endif
+__device__ V3_NOINLINE void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
                                                uint64_t* bar, bool with_hist) {
   const uint32_t scalars = sizeof(in.ep_len) + sizeof(in.cla) + k.n_terms * sizeof(in.esum[0]) + sizeof(in.origin) +
                            (k.curriculum ? sizeof(in.level) + sizeof(in.ttype) : 0);
@@ -168,7 +208,7 @@ __device__ __noinline__ void v3_issue_loads(V3In& in, const A1K& k, const ShifuA
 }
 
 // Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
-__device__ __noinline__ float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in, int e) {
+__device__ V3_NOINLINE float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in, int e) {
   const float* cmd = in.cla[0][e];
   const float* lin = in.cla[1][e];
   const float* ang = in.cla[2][e];
@@ -240,9 +280,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < V3_STAGES; ++b) {
       pipe::mbar_init(&s.full_in[b], 1);
       // every thread of the producing group arrives itself: no group barrier, fast warps move on
+      pipe::mbar_init(&s.e_done[b], 32);                     // yaw / xy of the tile's envs are in the ring
       pipe::mbar_init(&s.b_done[b], V3_BG_THREADS);
       pipe::mbar_init(&s.h_done[b], V3_C_THREADS);
     }
@@ -251,30 +292,33 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
   __syncthreads();
 
   // =========================================================================================
-  if (t >= V3_B_THREADS + V3_C_THREADS) {
+  if (t >= V3_DMA_BASE && t < V3_DMA_BASE + V3_DMA_THREADS) {
     // ---------------- DMA warp ----------------
-    if (t != V3_B_THREADS + V3_C_THREADS) return;
-    for (int j = 0; j < 2 && j < my_tiles; ++j) {
+    if (t != V3_DMA_BASE) return;
+    for (int j = 0; j < V3_STAGES && j < my_tiles; ++j) {
       V3_STAMP(s.t_issue[j]);
       v3_issue_loads(s.in[j], k, io, (long long)(first + j * stride) * A1_TILE, &s.full_in[j], true);
     }
     V3_T0(true);
     for (int j = 0; j < my_tiles; ++j) {
-      const int b = j & 1;
-      const uint32_t par = (j >> 1) & 1;
+      const int b = j % V3_STAGES;
+      const uint32_t par = (j / V3_STAGES) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       // input rows are dead once the head / history phase is over: store the pushed history and
       // refill the stage right away, long before the tile's height scan finishes
       V3_WAIT(V3_POLL_DMA, &s.h_done[b], par);
       V3_TICK(10);
+#ifdef V3_WI_DDELAY
+      v3_delay(V3_WI_DDELAY);
+#endif
       pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
       pipe::bulk_commit();
       V3_STAMP(s.t_issue[b]);
       // every other row of the stage is dead already: refill it while the store still reads hist
-      const long long en = (long long)(first + (j + 2) * stride) * A1_TILE;
-      if (j + 2 < my_tiles) v3_issue_loads(s.in[b], k, io, en, &s.full_in[b], false);
+      const long long en = (long long)(first + (j + V3_STAGES) * stride) * A1_TILE;
+      if (j + V3_STAGES < my_tiles) v3_issue_loads(s.in[b], k, io, en, &s.full_in[b], false);
       pipe::bulk_wait_read_all();
-      if (j + 2 < my_tiles) v3_issue_hist_load(s.in[b], io, en, &s.full_in[b]);
+      if (j + V3_STAGES < my_tiles) v3_issue_hist_load(s.in[b], io, en, &s.full_in[b]);
       V3_TICK(11);
       V3_COUNT(12);
     }
@@ -289,8 +333,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     V3_T0(g == 0 && lane == 0);
 
     for (int j = g; j < my_tiles; j += V3_B_GROUPS) {
-      const int b = j & 1;                                    // == g
-      const uint32_t par = (j >> 1) & 1;
+      const int b = j % V3_STAGES;
+      const uint32_t par = (j / V3_STAGES) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       const long long ge = e0 + lane;
       V3In& in = s.in[b];
@@ -300,19 +344,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       if (warp == 1) V3_SINCE(19, s.t_issue[b]);
       V3_TICK(warp == 0 ? 1 : 5);
 
-      // ---- B1: reward terms (warp w takes terms w, w+2, ...), termination, yaw normalisation
-      bool contact_term = false;
-#pragma unroll 1
-      for (int q = warp; q < k.n_terms; q += 2)
-#ifdef V3_WI_NOB1
-        s.rterm[g][q][lane] = 0.0f;
-#else
-        s.rterm[g][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane);
-#endif
-      if (warp == 0) {                                                    // a1_conditional.py:146-148
-        const float* fb = &in.contact[lane][k.base_body * 3];
-        contact_term = fma_rn(fb[2], fb[2], fma_rn(fb[1], fb[1], mul_rn(fb[0], fb[0]))) > k.contact_thr_sq;
-      } else {
+      // ---- B1: yaw normalisation for the scan first (warp 0; the scan group starts its index
+      //          arithmetic as soon as e_done completes), then the reward terms, split over the two
+      //          warps by the host-side cost balance k.term_warp
+      if (warp == 0) {
         // heights are measured at the PRE-reset pose (isaac_gym.py:320-322 runs before post_step)
         const ScanEnv ev = make_scan_env(in.root[lane]);
         const int q = lane >> 1, sl = lane & 1;
@@ -322,28 +357,42 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         a[sl] = ev.z2; a[2 + sl] = ev.z;
         bb[sl] = ev.w; bb[2 + sl] = ev.x;
         cc[sl] = ev.y;
+        pipe::mbar_arrive(&s.e_done[b]);
+      }
+#pragma unroll 1
+      for (int i = 0; i < k.term_count[warp]; ++i) {
+        const int q = k.term_list[warp][i];
+#ifdef V3_WI_NOB1
+        s.rterm[j & 1][q][lane] = 0.0f;
+#else
+        s.rterm[j & 1][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane);
+#endif
       }
       V3_TICK(warp == 0 ? 2 : 6);
       pipe::named_barrier(1 + g, V3_BG_THREADS);
       V3_TICK(warp == 0 ? 3 : 7);
 
-      // ---- B2: warp 0 — ordered accumulation, flags, reset, log sums
-      if (warp == 0) {
-        double st_sum[SHIFU_MAX_REWARD_TERMS];
+      // ---- B2: both warps decide termination (a1_conditional.py:146-150); warp 0 does the ordered
+      //          accumulation, flags and episode bookkeeping, warp 1 the state rewrite of resetting envs
+      long long len = in.ep_len[lane] + 1;                                 // env.py:95
+      const float* fb = &in.contact[lane][k.base_body * 3];
+      const bool contact_term = fma_rn(fb[2], fb[2], fma_rn(fb[1], fb[1], mul_rn(fb[0], fb[0]))) > k.contact_thr_sq;
+      const bool time_out = len > k.max_len;
+      const bool reset = contact_term | time_out;
+      double st_sum[SHIFU_MAX_REWARD_TERMS];
 #pragma unroll
-        for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) st_sum[q] = 0.0;
-        long long level_delta = 0;
-        long long len = in.ep_len[lane] + 1;                               // env.py:95
-        float esum[SHIFU_MAX_REWARD_TERMS];
+      for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) st_sum[q] = 0.0;
+      long long level_delta = 0;
+      float esum[SHIFU_MAX_REWARD_TERMS];
+      float cmd[3];
+      if (warp == 0) {
 #pragma unroll
         for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) esum[q] = (q < k.n_terms) ? in.esum[q][lane] : 0.0f;
-        const bool time_out = len > k.max_len;                             // a1_conditional.py:149
-        const bool reset = contact_term | time_out;
         float rew = 0.0f;                                                  // env.py:180-185
 #pragma unroll
         for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q) {
           if (q < k.n_terms) {
-            const float r = s.rterm[g][q][lane];
+            const float r = s.rterm[j & 1][q][lane];
             esum[q] = add_rn(esum[q], r);
             rew = add_rn(rew, r);
           }
@@ -352,21 +401,29 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         io.reset_buf[ge] = reset ? 1 : 0;
         io.time_out_buf[ge] = time_out ? 1 : 0;
         io.contact_term_buf[ge] = contact_term ? 1 : 0;
-        if (reset) {                                                       // env.py:101-102
-          float cmd[3] = {in.cla[0][lane][0], in.cla[0][lane][1], in.cla[0][lane][2]};
-          a1_reset_env<true>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
-                             st_sum, level_delta, in.origin[lane][0], in.origin[lane][1], in.origin[lane][2],
-                             k.curriculum ? in.level[lane] : 0, k.curriculum ? in.ttype[lane] : 0);
-          in.cla[0][lane][0] = cmd[0]; in.cla[0][lane][1] = cmd[1]; in.cla[0][lane][2] = cmd[2];
-        }
+        if (reset)                                                         // env.py:101-102, bookkeeping part
+          a1_reset_env<true, 2>(k, io, step, (int)ge, nullptr, nullptr, nullptr, cmd, esum, len, st_sum, level_delta,
+                                0.0f, 0.0f, 0.0f, 0, 0);
         io.ep_len[ge] = len;
 #pragma unroll
         for (int q = 0; q < SHIFU_MAX_REWARD_TERMS; ++q)
           if (q < k.n_terms) io.ep_sums[q][ge] = esum[q];
+        a1_log_sums<2>(k, reset, st_sum, level_delta, lane);
+      } else {
+        if (reset) {                                                       // state part
+          cmd[0] = in.cla[0][lane][0]; cmd[1] = in.cla[0][lane][1]; cmd[2] = in.cla[0][lane][2];
+          a1_reset_env<true, 1>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
+                                st_sum, level_delta, in.origin[lane][0], in.origin[lane][1], in.origin[lane][2],
+                                k.curriculum ? in.level[lane] : 0, k.curriculum ? in.ttype[lane] : 0);
+          in.cla[0][lane][0] = cmd[0]; in.cla[0][lane][1] = cmd[1]; in.cla[0][lane][2] = cmd[2];
+        }
         reinterpret_cast<float*>(&s.sC[rb][lane >> 1])[2 + (lane & 1)] =
             sub_rn(in.root[lane][2], k.h_off);                              // post-reset base z (D8)
-        a1_log_sums(k, reset, st_sum, level_delta, lane);
+        a1_log_sums<1>(k, reset, st_sum, level_delta, lane);
       }
+#ifdef V3_WI_BDELAY
+      v3_delay(V3_WI_BDELAY);
+#endif
       // post-reset rows / command / zb are final: hand the tile to the scan group
       pipe::mbar_arrive(&s.b_done[b]);
       V3_TICK(warp == 0 ? 13 : 14);
@@ -377,107 +434,71 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 
   // ---------------- scan group: thread = scan point ----------------
   {
-    const int p = t - V3_B_THREADS;                          // 0..191, points 187..191 idle
-    const float bx = k.px[p % A1_NX], by = k.py[(p / A1_NX) % A1_NY];
+    const int p = t - V3_SCAN_BASE;                          // index in the scan group
+    const int sw = p >> 5, lane = p & 31;
     const float hclip = fminf(k.h_clip, k.clip_obs);         // clip(clip(v,+-a),+-b) == clip(v,+-min(a,b))
     const unsigned max_px = (unsigned)(k.trows - 1), max_py = (unsigned)(k.tcols - 1);
     // banded index: (px>>3)*8*W + py*8 + (px&7)  ==  (px & ~7)*(W-1) + px + 8*py    (3 integer ops)
     const unsigned c1 = (unsigned)(k.band_w - 1);
     const short* __restrict__ table = k.table;
-    const f2_t BX = pk(bx, bx), BY = pk(by, by), NBY = pk(-by, -by), BORDER = pk(k.border, k.border);
+    const f2_t BORDER = pk(k.border, k.border);
     const f2_t RCP = pk(k.hdiv.r, k.hdiv.r), NEGD = pk(-k.hdiv.d, -k.hdiv.d), VS = pk(k.vscale, k.vscale);
     const f2_t NZ = pk(k.neg_zero, k.neg_zero);
+#ifdef V3_ADD_AS_FMA
+    // RN(a + b) == fma(a, 1, b) and RN(a - b) == fma(b, -1, a) exactly
+    const f2_t ONE = pk(k.one, k.one), NEG1 = pk(-k.one, -k.one);
+#define ADD2(a, b) fma2(a, ONE, b)
+#define SUB2(a, b) fma2(b, NEG1, a)
+#define MUL2(a, b) fma2(a, b, NZ)
+#elif defined(V3_ADD_SCALAR)
+    // packed adds split into two scalar adds (the light FMA pipe) — dev experiment
+    auto sadd2 = [](f2_t a, f2_t b) { float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(add_rn(a0, b0), add_rn(a1, b1)); };
+    auto ssub2 = [](f2_t a, f2_t b) { float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(sub_rn(a0, b0), sub_rn(a1, b1)); };
+#define ADD2(a, b) sadd2(a, b)
+#define SUB2(a, b) ssub2(a, b)
+#define MUL2(a, b) mul2(a, b)
+#else
+#define ADD2(a, b) add2(a, b)
+#define SUB2(a, b) sub2(a, b)
+#define MUL2(a, b) mul2(a, b)
+#endif
 #ifndef V3_F2I_CVT
     const f2_t DENORM = pk(__int_as_float(1), __int_as_float(1));     // 2^-149
 #endif
+    // Work items of a tile: (group of 32 scan points, batch of 8 envs).  6 scan warps: warp w owns
+    // point group w for the four env batches.  12 scan warps: warp w owns point group w % 6 for env
+    // batches 2*(w/6) and 2*(w/6)+1.
+    constexpr int V3_ITEMS = (V3_SCAN_WARPS == 12) ? 2 : 4;
     V3_T0(p == 0);
     for (int j = 0; j < my_tiles; ++j) {
-      const int b = j & 1;
-      const uint32_t par = (j >> 1) & 1;
+      const int b = j % V3_STAGES;
+      const uint32_t par = (j / V3_STAGES) & 1;
       const long long e0 = (long long)(first + j * stride) * A1_TILE;
       const int rb = j & 3;
-      V3_WAIT(V3_POLL_SCAN, &s.b_done[b], par);
+      V3_WAIT(V3_POLL_SCAN, &s.e_done[b], par);
       V3_TICK(16);
-      // ---- obs head (a1_conditional.py:131-144) + history push (train.py:12-14): post-reset rows
       {
-        V3In& in = s.in[b];
-        const float c = k.clip_obs;
-        for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
-          const int e = i / A1_DOF, d = i - e * A1_DOF;
-          float* h = io.obs_buf + (e0 + e) * A1_OBS;
-          const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
-          const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
-                      a2 = in.hist[e][d * A1_HIST + 2];
-#ifndef V3_WI_NOHEAD
-          __stcs(h + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
-          __stcs(h + 24 + d, clampf(qd.y, -c, c));
-          __stcs(h + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
-          __stcs(h + 48 + d, clampf(a1, -c, c));
-          __stcs(h + 60 + d, clampf(a2, -c, c));
-#endif
-          in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
-          in.hist[e][d * A1_HIST + 1] = a0;
-          in.hist[e][d * A1_HIST + 0] = in.act[e][d];
-        }
-        for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
-          const int e = i / 12, q = i - e * 12;
-          const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
-#ifndef V3_WI_NOHEAD
-          __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
-#endif
-        }
-        // carried body-frame velocities for the next control step (robot.py:222-229, D7): one
-        // rotation per (env, vector) item on half of the scan warps, the halves alternating from tile
-        // to tile so that no warp is permanently the slowest of the group
-#ifdef V3_CARRY_ONE_WARP
-        if (io.carry_body_frame && p >= V3_C_THREADS - 32) {
-          const int e = p - (V3_C_THREADS - 32);
-          const long long ge = e0 + e;
-          const float* r = in.root[e];
-          float o[3];
-          rotate_inverse(r + 3, r[7], r[8], r[9], o);
-          io.base_lin_vel[ge * 3 + 0] = o[0]; io.base_lin_vel[ge * 3 + 1] = o[1]; io.base_lin_vel[ge * 3 + 2] = o[2];
-          rotate_inverse(r + 3, r[10], r[11], r[12], o);
-          io.base_ang_vel[ge * 3 + 0] = o[0]; io.base_ang_vel[ge * 3 + 1] = o[1]; io.base_ang_vel[ge * 3 + 2] = o[2];
-          rotate_inverse(r + 3, 0.0f, 0.0f, -1.0f, o);
-          io.projected_gravity[ge * 3 + 0] = o[0]; io.projected_gravity[ge * 3 + 1] = o[1];
-          io.projected_gravity[ge * 3 + 2] = o[2];
-        }
-#else
-        if (io.carry_body_frame) {
-          const int it = p - ((j & 1) ? 96 : 0);                 // item = (vector, env): 3 x 32
-          if (it >= 0 && it < 96) {
-            const int v = it >> 5, e = it & 31;
-            const long long ge = e0 + e;
-            const float* r = in.root[e];
-            float o[3];
-            rotate_inverse(r + 3, v == 2 ? 0.0f : r[7 + 3 * v], v == 2 ? 0.0f : r[8 + 3 * v],
-                           v == 2 ? -1.0f : r[9 + 3 * v], o);
-            float* dst = (v == 0 ? io.base_lin_vel : (v == 1 ? io.base_ang_vel : io.projected_gravity)) + ge * 3;
-            dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
-          }
-        }
-#endif
-      }
-      pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
-      pipe::mbar_arrive(&s.h_done[b]);
-      V3_TICK(9);
-#ifdef V3_WI_NOSCAN
-      if (p < 0) {
-#else
-      if (p < A1_POINTS) {
-#endif
-        float* ob = io.obs_buf + e0 * A1_OBS + A1_HEAD + p;
-        float* mb = HAS_MROW ? io.measured_heights + e0 * A1_POINTS + p : nullptr;
-        // Batches of 8 envs (4 pairs): index arithmetic in packed fp32x2 (two envs per
-        // instruction), then the 8 table gathers back to back.  The four batches of a tile are
-        // software-pipelined in registers: batch i+1's arithmetic and gathers are issued before
-        // batch i's gathered heights are consumed, so the gather latency overlaps arithmetic.
-        auto index_batch = [&](int q0, unsigned (&idx)[8]) {
+        // item -> (scan point of this lane, first env pair of the batch)
+        struct Item { float bx, by; int q0, pt; bool live; };
+        auto item = [&](int it) {
+          int g, qb;
+          if (V3_SCAN_WARPS == 12) { g = sw % 6; qb = 2 * (sw / 6) + it; }
+          else { g = sw; qb = it; }
+          Item r;
+          const int raw = 32 * g + lane;
+          r.live = raw < A1_POINTS;
+          r.pt = r.live ? raw : A1_POINTS - 1;                // idle lanes shadow the last point, stores masked
+          r.bx = k.px[r.pt % A1_NX]; r.by = k.py[r.pt / A1_NX];
+          r.q0 = 4 * qb;
+          return r;
+        };
+        // Index arithmetic of one item in packed fp32x2 (two envs per instruction).
+        auto index_batch = [&](const Item& w, unsigned (&idx)[8]) {
+          const f2_t BX = pk(w.bx, w.bx), BY = pk(w.by, w.by), NBY = pk(-w.by, -w.by);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float4 a = s.sA[rb][q0 + u], bq = s.sB[rb][q0 + u];
-            const float2 cq = *reinterpret_cast<const float2*>(&s.sC[rb][q0 + u]);
+            const float4 a = s.sA[rb][w.q0 + u], bq = s.sB[rb][w.q0 + u];
+            const float2 cq = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u]);
             const f2_t Z2 = pk(a.x, a.y), Z = pk(a.z, a.w), W = pk(bq.x, bq.y), X = pk(bq.z, bq.w);
             const f2_t Y = pk(cq.x, cq.y);
             // quat_apply_yaw (shifu/utils/terrain.py:202-206) on (bx, by, 0):
@@ -486,11 +507,11 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding) even under --fmad=false,
             // which flips ~0.3 % of the cell indices; fma(a, b, -0) == RN(a*b) exactly and cannot be
             // contracted again (NZ comes from a kernel parameter, so it is not constant-folded).
-            const f2_t tx = mul2(Z2, NBY), ty = mul2(Z2, BX);
-            const f2_t rx = sub2(add2(BX, fma2(W, tx, NZ)), fma2(Z, ty, NZ));
-            const f2_t ry = add2(add2(BY, fma2(W, ty, NZ)), fma2(Z, tx, NZ));
+            const f2_t tx = MUL2(Z2, NBY), ty = MUL2(Z2, BX);
+            const f2_t rx = SUB2(ADD2(BX, fma2(W, tx, NZ)), fma2(Z, ty, NZ));
+            const f2_t ry = ADD2(ADD2(BY, fma2(W, ty, NZ)), fma2(Z, tx, NZ));
             // + base xy, + border, / horizontal_scale (isaac_gym.py:416-421)
-            const f2_t ax = add2(add2(rx, X), BORDER), ay = add2(add2(ry, Y), BORDER);
+            const f2_t ax = ADD2(ADD2(rx, X), BORDER), ay = ADD2(ADD2(ry, Y), BORDER);
             unsigned px0, px1, py0, py1;
             if (EXACT_DIV) {
               float a0, a1, b0, b1;
@@ -501,7 +522,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
               py0 = min(__float2uint_rz(div_rn(b0, k.hdiv.d)), max_py);
               py1 = min(__float2uint_rz(div_rn(b1, k.hdiv.d)), max_py);
             } else {                         // q0 = x*r; e = fma(-d, q0, x); q = fma(e, r, q0)
-              const f2_t qx = mul2(ax, RCP), qy = mul2(ay, RCP);
+              const f2_t qx = MUL2(ax, RCP), qy = MUL2(ay, RCP);
               const f2_t fx = fma2(fma2(NEGD, qx, ax), RCP, qx), fy = fma2(fma2(NEGD, qy, ay), RCP, qy);
 #ifndef V3_F2I_CVT
               // .long() + clip without the conversion unit: RZ(f * 2^-149) is the denormal whose bit
@@ -527,18 +548,16 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 8; ++u) h[u] = v3_gather(table + idx[u]);      // isaac_gym.py:427-431 (folded)
         };
-        auto gather_batch = [&](int q0, int (&h)[8]) {
-          unsigned idx[8];
-          index_batch(q0, idx);
-          load_batch(idx, h);
-        };
-        auto store_batch = [&](int q0, const int (&h)[8]) {
+        auto store_batch = [&](const Item& w, const int (&h)[8]) {
+          float* ob = io.obs_buf + (e0 + 2 * w.q0) * A1_OBS + A1_HEAD + w.pt;
+          float* mb = HAS_MROW ? io.measured_heights + (e0 + 2 * w.q0) * A1_POINTS + w.pt : nullptr;
+          if (!w.live) return;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][q0 + u].z);
+            const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u].z);
             const f2_t hg = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
             float v0, v1;
-            upk(sub2(pk(zb.x, zb.y), hg), v0, v1);                            // (z - 0.5) - h, a1_conditional.py:132
+            upk(SUB2(pk(zb.x, zb.y), hg), v0, v1);                            // (z - 0.5) - h, a1_conditional.py:132
             v3_store(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
             v3_store(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
             if (HAS_MROW) {
@@ -548,45 +567,83 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
               __stcs(mb + (2 * u + 1) * A1_POINTS, g1);
             }
           }
-          ob += 8 * A1_OBS;
-          if (HAS_MROW) mb += 8 * A1_POINTS;
         };
-#if defined(V3_NO_PIPE_SCAN)
-#pragma unroll 1
-        for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
-          int h[8];
-          gather_batch(q0, h);
-          store_batch(q0, h);
-        }
-#elif defined(V3_MOVE_PIPE)
-        // rolled on purpose: the loop body (one gather_batch + one store_batch) stays small enough
-        // for the instruction cache shared with the other warp roles
-        int hc[8];   // sign-extended int16 cells: plain register moves below, no 16-bit packing
-        gather_batch(0, hc);
-#pragma unroll 1
-        for (int q0 = 0; q0 < A1_TILE / 2; q0 += 4) {
-          int hn[8];
-          if (q0 + 4 < A1_TILE / 2) gather_batch(q0 + 4, hn);
-          store_batch(q0, hc);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) hc[u] = hn[u];
-        }
-#else
         // Rolled software pipeline (the body stays small enough for the instruction cache shared with
-        // the other warp roles): the gathers of batch i are issued at the END of a trip and consumed
-        // in the MIDDLE of the next one, after the index arithmetic of batch i+1 — so their L1/L2
-        // latency hides under ~200 instructions of independent math, with no register copies.
+        // the other warp roles): the gathers of item i are issued at the END of a trip and consumed
+        // in the MIDDLE of the next one, after the index arithmetic of item i+1 — so their L1/L2
+        // latency hides under ~200 instructions of independent math, with no register copies.  The
+        // first item's gathers are issued BEFORE the head phase, which hides them as well.
         unsigned idx[8];
         int h[8];    // sign-extended int16 cells
-        index_batch(0, idx);
+        Item cur = item(0);
+#ifndef V3_WI_NOSCAN
+        index_batch(cur, idx);
         load_batch(idx, h);
-#pragma unroll 1
-        for (int q0 = 0; q0 < A1_TILE / 2 - 4; q0 += 4) {
-          index_batch(q0 + 4, idx);
-          store_batch(q0, h);
-          load_batch(idx, h);
+#endif
+        // ---- obs head (a1_conditional.py:131-144) + history push (train.py:12-14): post-reset rows
+        V3_TICK(20);
+        V3_WAIT(V3_POLL_SCAN, &s.b_done[b], par);
+        V3_TICK(8);
+        {
+          V3In& in = s.in[b];
+          const float c = k.clip_obs;
+          for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
+            const int e = i / A1_DOF, d = i - e * A1_DOF;
+            float* hrow = io.obs_buf + (e0 + e) * A1_OBS;
+            const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
+            const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
+                        a2 = in.hist[e][d * A1_HIST + 2];
+#ifndef V3_WI_NOHEAD
+            __stcs(hrow + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
+            __stcs(hrow + 24 + d, clampf(qd.y, -c, c));
+            __stcs(hrow + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
+            __stcs(hrow + 48 + d, clampf(a1, -c, c));
+            __stcs(hrow + 60 + d, clampf(a2, -c, c));
+#endif
+            in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
+            in.hist[e][d * A1_HIST + 1] = a0;
+            in.hist[e][d * A1_HIST + 0] = in.act[e][d];
+          }
+          for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
+            const int e = i / 12, q = i - e * 12;
+            const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
+#ifndef V3_WI_NOHEAD
+            __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
+#endif
+          }
+          // carried body-frame velocities for the next control step (robot.py:222-229, D7): one
+          // rotation per (env, vector) item on half of the scan warps, the halves alternating from tile
+          // to tile so that no warp is permanently the slowest of the group
+          if (io.carry_body_frame) {
+            const int it = p - ((j & 1) ? V3_C_THREADS / 2 : 0);  // item = (vector, env): 3 x 32
+            if (it >= 0 && it < 96) {
+              const int v = it >> 5, e = it & 31;
+              const long long ge = e0 + e;
+              const float* r = in.root[e];
+              float o[3];
+              rotate_inverse(r + 3, v == 2 ? 0.0f : r[7 + 3 * v], v == 2 ? 0.0f : r[8 + 3 * v],
+                             v == 2 ? -1.0f : r[9 + 3 * v], o);
+              float* dst = (v == 0 ? io.base_lin_vel : (v == 1 ? io.base_ang_vel : io.projected_gravity)) + ge * 3;
+              dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+            }
+          }
         }
-        store_batch(A1_TILE / 2 - 4, h);
+        pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
+        pipe::mbar_arrive(&s.h_done[b]);
+        V3_TICK(9);
+#ifdef V3_WI_SDELAY
+        v3_delay(V3_WI_SDELAY);
+#endif
+#ifndef V3_WI_NOSCAN
+#pragma unroll 1
+        for (int it = 1; it < V3_ITEMS; ++it) {
+          const Item nxt = item(it);
+          index_batch(nxt, idx);
+          store_batch(cur, h);
+          load_batch(idx, h);
+          cur = nxt;
+        }
+        store_batch(cur, h);
 #endif
       }
       V3_TICK(17);

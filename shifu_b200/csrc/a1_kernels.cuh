@@ -45,6 +45,8 @@ struct A1K {
   int rp_pow2[SHIFU_MAX_REWARD_TERMS];
   // largest s with sqrt_rn(s) <= threshold: "norm > thr" == "sum of squares > thr_sq" exactly
   float rp_thr_sq[SHIFU_MAX_REWARD_TERMS];
+  // term lists of the two B warps of the pipelined kernel (host-side cost balance)
+  int term_count[2], term_list[2][SHIFU_MAX_REWARD_TERMS];
   float contact_thr_sq;
   // scan table
   const short* table;     // tiled min-of-3 table
@@ -53,6 +55,7 @@ struct A1K {
   int tiled;              // 1: banded (T[px>>3][py][px&7], a 128-B line = 8x8 cells), 0: row-major (pitch = tcols)
   double* stats;          // SHIFU_NUM_STATS accumulators
   float neg_zero;         // -0.0f, opaque to ptxas: see mulx2() in a1_fused_tma.cuh
+  float one;              // 1.0f, opaque to ptxas (packed adds issued as fma(a, 1, b) on the FMA pipe)
 };
 
 __device__ __forceinline__ float hdivide(float x, const A1K& k) {
@@ -258,7 +261,9 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <bool MIRROR>
+// PARTS: 1 = state rewrite (curriculum, dof / root rows, push force, history, command), 2 = episode
+// bookkeeping (length, episode sums -> log sums); the pipelined kernel runs the two on different warps.
+template <bool MIRROR, int PARTS = 3>
 __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& io, long long step, int ge,
                                              float* root_row, float* dof_row, float* hist_row,
                                              float (&cmd)[3], float (&esum)[SHIFU_MAX_REWARD_TERMS],
@@ -268,6 +273,14 @@ __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& 
   // (ox, oy, oz) = env_origins[ge], old_level = terrain_levels[ge], ty = terrain_types[ge]: read by
   // the caller (global memory, or the shared-memory stage the pipelined kernel bulk-loads them into)
   const long long gid = k.env_offset + ge;
+  if (PARTS & 2) {                                                       // env.py:119-122 ; log_info, env.py:149-153
+    len = 0;
+#pragma unroll
+    for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
+      if (j < k.n_terms) { st_sum[j] = (double)esum[j]; esum[j] = 0.0f; }
+    }
+  }
+  if (!(PARTS & 1)) return;
   if (k.curriculum) {                                                    // a1_conditional.py:204-221
     const float dist = norm2_fma(sub_rn(root_row[0], ox), sub_rn(root_row[1], oy));
     const bool up = dist > k.up_dist;
@@ -316,14 +329,9 @@ __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& 
   fr[0] = add_rn(mul_rn(k.force_span, u01(uf.x)), k.force_low);
   fr[1] = add_rn(mul_rn(k.force_span, u01(uf.y)), k.force_low);
   fr[2] = add_rn(mul_rn(k.force_span, u01(uf.z)), k.force_low);
-  // ShifuVecEnv.reset_idx, env.py:119-122 ; log_info, env.py:149-153
-  len = 0;
+  // HistoryRecorder.reset_idx, train.py:16-17
 #pragma unroll
   for (int j = 0; j < A1_DOF * A1_HIST; ++j) hist_row[j] = 0.0f;
-#pragma unroll
-  for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
-    if (j < k.n_terms) { st_sum[j] = (double)esum[j]; esum[j] = 0.0f; }
-  }
   // sample_command, a1_conditional.py:194-200
   const U4 uc = draw(k.seed, gid, step, STREAM_CMD);
   cmd[0] = add_rn(mul_rn(k.cmd_span[0], u01(uc.x)), k.cmd_low[0]);
@@ -333,10 +341,23 @@ __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& 
 }
 
 // Warp-level reduction of the per-step log sums (env.py:149-153) -> one set of atomics per warp.
+template <int PARTS = 3>
 __device__ __forceinline__ void a1_log_sums(const A1K& k, bool reset, const double (&st_sum)[SHIFU_MAX_REWARD_TERMS],
                                             long long level_delta, int lane) {
   const unsigned any = __ballot_sync(0xffffffffu, reset);
   if (!any) return;
+  if (PARTS != 3) {              // split form (pipelined kernel): direct reductions only
+    if (reset) {
+      if (PARTS & 2) {
+#pragma unroll
+        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j)
+          if (j < k.n_terms) atomicAdd(k.stats + SHIFU_STAT_TERM0 + j, st_sum[j]);
+        atomicAdd(k.stats + SHIFU_STAT_NRESET, 1.0);
+      }
+      if ((PARTS & 1) && level_delta != 0) atomicAdd(k.stats + SHIFU_STAT_LEVEL_SUM, (double)level_delta);
+    }
+    return;
+  }
   if (__popc(any) <= 4) {
     // sparse resets (the steady state, ~1 % of envs): a handful of fire-and-forget reductions is
     // cheaper for the latency-critical warp than seven 5-step double-precision warp reductions

@@ -43,6 +43,85 @@ __device__ __forceinline__ void abb_box_reset(float* row, const AbbK& k, long lo
   for (int j = 7; j < 13; ++j) row[j] = 0.0f;
 }
 
+// ShifuVecEnv.reset_idx for one env of the 4-actor scene (env.py:114-130, robot.py:74-77,
+// units.py:130-134, a_prior_stage.py:39-51): robot dofs / root, table root, random cube and goal.
+__device__ __forceinline__ void abb_reset_env(const AbbK& k, const ShifuAbbStepIO& io, long long step, int e,
+                                              float* cube, float* goal) {
+  const long long gid = k.env_offset + e;
+  for (int d = 0; d < k.n_dof; ++d) {                               // robot.py:74-77
+    io.dof_state[((long long)e * k.n_dof + d) * 2 + 0] = k.q0[d];
+    io.dof_state[((long long)e * k.n_dof + d) * 2 + 1] = 0.0f;
+    io.dof_targets[(long long)e * k.n_dof + d] = k.q0[d];
+  }
+  float* rob = io.root_state + ((long long)e * k.n_actors + k.robot_actor) * 13;   // units.py:130-134
+  float* tab = io.root_state + ((long long)e * k.n_actors + k.table_actor) * 13;
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    rob[j] = (j < 7) ? k.robot_root[j] : 0.0f;
+    tab[j] = (j < 7) ? k.table_root[j] : 0.0f;
+  }
+  abb_box_reset(cube, k, gid, step, STREAM_CUBE_POS, STREAM_CUBE_EUL, k.pos_low[2]);
+  abb_box_reset(goal, k, gid, step, STREAM_GOAL_POS, STREAM_GOAL_EUL, k.goal_z);
+}
+
+// Warp-level reduction of the per-step log sums -> one set of atomics per warp.
+__device__ __forceinline__ void abb_log_sums(const AbbK& k, bool reset, bool success,
+                                             const double (&st_sum)[SHIFU_MAX_REWARD_TERMS], int lane) {
+  const unsigned any = __ballot_sync(0xffffffffu, reset);
+  if (!any) return;
+  double cnt = reset ? 1.0 : 0.0, suc = (reset && success) ? 1.0 : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    suc += __shfl_xor_sync(0xffffffffu, suc, o);
+  }
+#pragma unroll
+  for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
+    if (j < k.n_terms) {
+      double v = st_sum[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(k.stats + SHIFU_STAT_TERM0 + j, v);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(k.stats + SHIFU_STAT_NRESET, cnt);
+    atomicAdd(k.stats + SHIFU_STAT_SUCCESS, suc);
+  }
+}
+
+// Stand-alone reset_idx(env_ids) (ShifuVecEnv.reset, env.py:108-112, and user calls): one thread per
+// id; ids == nullptr means arange(n_ids).  The logged success rate is the mean of the CURRENT
+// success_buf over the ids (a_prior_stage.py:92-93).
+__global__ void __launch_bounds__(128)
+abb_reset_idx_kernel(const __grid_constant__ AbbK k, const __grid_constant__ ShifuAbbStepIO io,
+                     const long long* __restrict__ ids, int n_ids) {
+  const int lane = threadIdx.x & 31;
+  const long long step = (io.step_dev != nullptr) ? *io.step_dev : io.step;
+  for (int i0 = blockIdx.x * blockDim.x; i0 < n_ids; i0 += gridDim.x * blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    bool reset = false, success = false;
+    double st_sum[SHIFU_MAX_REWARD_TERMS];
+#pragma unroll
+    for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) st_sum[j] = 0.0;
+    if (i < n_ids) {
+      const int e = (ids != nullptr) ? (int)ids[i] : i;
+      if (e >= 0 && e < k.n) {
+        reset = true;
+        success = io.success_buf[e] != 0;
+        abb_reset_env(k, io, step, e, io.root_state + ((long long)e * k.n_actors + k.cube_actor) * 13,
+                      io.root_state + ((long long)e * k.n_actors + k.goal_actor) * 13);
+        io.ep_len[e] = 0;
+        io.reset_buf[e] = 1;
+#pragma unroll
+        for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j)
+          if (j < k.n_terms) { st_sum[j] = (double)io.ep_sums[j][e]; io.ep_sums[j][e] = 0.0f; }
+      }
+    }
+    abb_log_sums(k, reset, success, st_sum, lane);
+  }
+}
+
 __global__ void __launch_bounds__(128)
 abb_post_physics_kernel(const __grid_constant__ AbbK k, const __grid_constant__ ShifuAbbStepIO io) {
   const int lane = threadIdx.x & 31;
@@ -91,21 +170,7 @@ abb_post_physics_kernel(const __grid_constant__ AbbK k, const __grid_constant__ 
       io.time_out_buf[e] = time_out ? 1 : 0;
       io.success_buf[e] = success ? 1 : 0;
       if (reset) {                                                        // env.py:114-130
-        const long long gid = k.env_offset + e;
-        for (int d = 0; d < k.n_dof; ++d) {                               // robot.py:74-77
-          io.dof_state[((long long)e * k.n_dof + d) * 2 + 0] = k.q0[d];
-          io.dof_state[((long long)e * k.n_dof + d) * 2 + 1] = 0.0f;
-          io.dof_targets[(long long)e * k.n_dof + d] = k.q0[d];
-        }
-        float* rob = io.root_state + ((long long)e * k.n_actors + k.robot_actor) * 13;   // units.py:130-134
-        float* tab = io.root_state + ((long long)e * k.n_actors + k.table_actor) * 13;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          rob[j] = (j < 7) ? k.robot_root[j] : 0.0f;
-          tab[j] = (j < 7) ? k.table_root[j] : 0.0f;
-        }
-        abb_box_reset(cube, k, gid, step, STREAM_CUBE_POS, STREAM_CUBE_EUL, k.pos_low[2]);
-        abb_box_reset(goal, k, gid, step, STREAM_GOAL_POS, STREAM_GOAL_EUL, k.goal_z);
+        abb_reset_env(k, io, step, e, cube, goal);
         cx = cube[0]; cy = cube[1]; gx = goal[0]; gy = goal[1];
         len = 0;
 #pragma unroll
@@ -122,28 +187,7 @@ abb_post_physics_kernel(const __grid_constant__ AbbK k, const __grid_constant__ 
       o[0] = clampf(cx, -c, c); o[1] = clampf(cy, -c, c); o[2] = clampf(gx, -c, c);
       o[3] = clampf(gy, -c, c); o[4] = clampf(ex, -c, c); o[5] = clampf(ey, -c, c);
     }
-    const unsigned any = __ballot_sync(0xffffffffu, reset);
-    if (any) {
-      double cnt = reset ? 1.0 : 0.0, suc = (reset && success) ? 1.0 : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        suc += __shfl_xor_sync(0xffffffffu, suc, o);
-      }
-#pragma unroll
-      for (int j = 0; j < SHIFU_MAX_REWARD_TERMS; ++j) {
-        if (j < k.n_terms) {
-          double v = st_sum[j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) atomicAdd(k.stats + SHIFU_STAT_TERM0 + j, v);
-        }
-      }
-      if (lane == 0) {
-        atomicAdd(k.stats + SHIFU_STAT_NRESET, cnt);
-        atomicAdd(k.stats + SHIFU_STAT_SUCCESS, suc);
-      }
-    }
+    abb_log_sums(k, reset, success, st_sum, lane);
   }
 }
 

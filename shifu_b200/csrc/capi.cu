@@ -143,7 +143,7 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   k.xy_span = (float)((double)d.reset_xy_range - (double)(-d.reset_xy_range)); k.xy_low = -d.reset_xy_range;
   k.force_span = (float)((double)d.push_force_max - (double)(-d.push_force_max)); k.force_low = -d.push_force_max;
   for (int i = 0; i < 3; ++i) { k.cmd_span[i] = (float)((double)d.cmd_high[i] - (double)d.cmd_low[i]); k.cmd_low[i] = d.cmd_low[i]; }
-  k.neg_zero = -0.0f;
+  k.neg_zero = -0.0f; k.one = 1.0f;
   k.curriculum = d.curriculum; k.max_level = d.max_terrain_level; k.n_types = d.num_terrain_types;
   k.up_dist = d.level_up_distance; k.down_factor = d.level_down_factor;
   k.n_terms = d.num_reward_terms;
@@ -157,6 +157,21 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
     k.rp_thr_sq[i] = sqrt_threshold(p1);
   }
   k.contact_thr_sq = sqrt_threshold(d.contact_term_force);
+  // Split of the term list over the two B warps of the pipelined kernel: longest-processing-time
+  // greedy on rough per-term instruction counts; warp 0 also carries the yaw normalisation (~60).
+  static const int term_cost[] = {30, 25, 12, 135, 70, 40, 20, 20};
+  int load[2] = {60, 0}, order[SHIFU_MAX_REWARD_TERMS];
+  for (int i = 0; i < k.n_terms; ++i) order[i] = i;
+  auto cost_of = [&](int q) { const int c = k.terms[q]; return (c >= 0 && c < 8) ? term_cost[c] : 40; };
+  for (int i = 0; i < k.n_terms; ++i)
+    for (int j = i + 1; j < k.n_terms; ++j)
+      if (cost_of(order[j]) > cost_of(order[i])) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  k.term_count[0] = k.term_count[1] = 0;
+  for (int i = 0; i < k.n_terms; ++i) {
+    const int w = load[1] < load[0] ? 1 : 0;
+    k.term_list[w][k.term_count[w]++] = order[i];
+    load[w] += cost_of(order[i]);
+  }
   return SHIFU_OK;
 }
 
@@ -472,6 +487,21 @@ extern "C" int shifu_abb_post_physics(ShifuCtx* c, const ShifuAbbStepIO* io, voi
   return SHIFU_OK;
 }
 
+extern "C" int shifu_abb_reset_idx(ShifuCtx* c, const ShifuAbbStepIO* io, const int64_t* ids, int32_t n_ids, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io);
+  if (c->is_a1) return fail(SHIFU_E_STATE, "shifu_abb_reset_idx needs an ABB ctx");
+  if (n_ids < 0 || n_ids > c->abb.num_envs) return fail(SHIFU_E_RANGE, "n_ids=%d out of range", n_ids);
+  if (n_ids == 0) return SHIFU_OK;                    // shifu/gym/env.py:115-116
+  REQUIRE_PTR(io->root_state); REQUIRE_PTR(io->dof_state); REQUIRE_PTR(io->dof_targets); REQUIRE_PTR(io->ep_len);
+  REQUIRE_PTR(io->reset_buf); REQUIRE_PTR(io->success_buf);
+  for (int j = 0; j < c->abb.num_reward_terms; ++j)
+    if (io->ep_sums[j] == nullptr) return fail(SHIFU_E_NULL, "ep_sums[%d] is NULL", j);
+  abb_reset_idx_kernel<<<grid_for(n_ids, 128, c->sm_count, 16), 128, 0, S(stream)>>>(
+      c->abbk, *io, reinterpret_cast<const long long*>(ids), n_ids);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
 extern "C" int shifu_compact_reset_ids(ShifuCtx* c, const uint8_t* flags, int32_t n, int64_t* ids, int32_t* n_out, void* stream) {
   REQUIRE_PTR(c); REQUIRE_PTR(flags); REQUIRE_PTR(ids); REQUIRE_PTR(n_out);
   if (n <= 0) return fail(SHIFU_E_RANGE, "n must be > 0 (got %d)", n);
@@ -563,7 +593,21 @@ extern "C" int shifu_publish_extras(ShifuCtx* c, const double* stats, float* ext
   REQUIRE_PTR(c); REQUIRE_PTR(stats); REQUIRE_PTR(extras);
   const float ls = c->is_a1 ? c->a1.max_episode_length_s : c->abb.max_episode_length_s;
   const int nt = c->is_a1 ? c->a1.num_reward_terms : c->abb.num_reward_terms;
-  publish_extras_kernel<<<1, 32, 0, S(stream)>>>(stats, extras, ls, nt);
+  publish_extras_kernel<<<1, 32, 0, S(stream)>>>(stats, extras, 1, 0, nullptr, ls, nt);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_publish_extras_ring(ShifuCtx* c, const double* stats, float* ring, int32_t slots, int32_t slot,
+                                         const int64_t* step_dev, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(stats); REQUIRE_PTR(ring);
+  if (slots < 1) return fail(SHIFU_E_RANGE, "slots must be >= 1 (got %d)", slots);
+  if (slot >= slots) return fail(SHIFU_E_RANGE, "slot %d outside the ring of %d", slot, slots);
+  if (slot < 0 && step_dev == nullptr) return fail(SHIFU_E_NULL, "slot < 0 needs the device step counter");
+  const float ls = c->is_a1 ? c->a1.max_episode_length_s : c->abb.max_episode_length_s;
+  const int nt = c->is_a1 ? c->a1.num_reward_terms : c->abb.num_reward_terms;
+  publish_extras_kernel<<<1, 32, 0, S(stream)>>>(stats, ring, slots, slot, reinterpret_cast<const long long*>(step_dev),
+                                                 ls, nt);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }

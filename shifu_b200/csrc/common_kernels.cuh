@@ -158,20 +158,31 @@ __global__ void collect_stats_kernel(double* __restrict__ acc, double* __restric
 // extras["episode"]: mean over reset envs / max_episode_length_s (env.py:149-153), left untouched
 // when nobody reset (env.py:115-116); terrain_levels mean over all envs (a1_conditional.py:126-129);
 // success_rate = mean over reset envs (a_prior_stage.py:92-93).
-__global__ void publish_extras_kernel(const double* __restrict__ stats, float* __restrict__ extras,
-                                      float max_len_s, int n_terms) {
+// The output is a ring of `slots` arrays of SHIFU_NUM_STATS floats: each step publishes into its own
+// slot (slot < 0: derived from the device step counter, for graph-replayed steps), so the dicts a
+// caller keeps from earlier steps (rsl_rl keeps 24) stay distinct; a step without resets copies the
+// previous slot (the reference keeps the same dict alive).  slots == 1 is the in-place form.
+__global__ void publish_extras_kernel(const double* __restrict__ stats, float* __restrict__ ring, int slots, int slot,
+                                      const long long* __restrict__ step_dev, float max_len_s, int n_terms) {
   const int i = threadIdx.x;
   if (i >= SHIFU_NUM_STATS) return;
+  if (slot < 0) slot = (int)((*step_dev - 1) % slots);
+  const int prev = (slot + slots - 1) % slots;
+  float* extras = ring + (size_t)slot * SHIFU_NUM_STATS;
+  const float* old = ring + (size_t)prev * SHIFU_NUM_STATS;
   const double nreset = stats[SHIFU_STAT_NRESET];
   if (i == SHIFU_STAT_NRESET) { extras[i] = (float)nreset; return; }
-  if (nreset <= 0.0) return;
-  if (i < SHIFU_MAX_REWARD_TERMS) {
-    if (i < n_terms) extras[i] = div_rn((float)(stats[i] / nreset), max_len_s);
-  } else if (i == SHIFU_STAT_LEVEL_SUM) {
-    extras[i] = (float)(stats[i] / stats[SHIFU_STAT_NENVS]);
-  } else if (i == SHIFU_STAT_SUCCESS) {
-    extras[i] = (float)(stats[i] / nreset);
+  float v = old[i];
+  if (nreset > 0.0) {
+    if (i < SHIFU_MAX_REWARD_TERMS) {
+      if (i < n_terms) v = div_rn((float)(stats[i] / nreset), max_len_s);
+    } else if (i == SHIFU_STAT_LEVEL_SUM) {
+      v = (float)(stats[i] / stats[SHIFU_STAT_NENVS]);
+    } else if (i == SHIFU_STAT_SUCCESS) {
+      v = (float)(stats[i] / nreset);
+    }
   }
+  extras[i] = v;
 }
 
 __global__ void level_sum_kernel(const long long* __restrict__ levels, int n, double* __restrict__ out) {

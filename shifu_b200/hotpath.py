@@ -216,6 +216,69 @@ class EnvKernels:
                                            nv.ptr(ang), nv.ptr(pg), nv.ptr(gvec), nv.current_stream()))
 
 
+EXTRAS_SLOTS = 64      # ring of per-step extras arrays (rsl_rl holds the dicts of one 24-step rollout)
+
+
+class _StepStats:
+    """Per-step statistics -> ``extras`` plumbing shared by the two hot paths.
+
+    Every step publishes into its own slot of ``extras_ring`` so the dict returned for step t is
+    not overwritten by step t+1 (the reference allocates fresh tensors whenever somebody resets,
+    env.py:124-130).  In sharded runs the 16-double all-reduce and the publish run on a side
+    stream: the next step's kernels never wait for the collective; the main stream
+    re-joins at the start of the next step (``wait_stats``), by which time it has long finished."""
+
+    def _init_stats(self, dev):
+        self.stats_ring = torch.zeros(EXTRAS_SLOTS, nv.NUM_STATS, device=dev, dtype=torch.double)
+        self.extras_ring = torch.zeros(EXTRAS_SLOTS, nv.NUM_STATS, device=dev, dtype=torch.float)
+        self._stats_slot = 0
+        self._side = None
+        self._pending = None
+
+    @property
+    def slot(self) -> int:
+        return self.step_counter % EXTRAS_SLOTS
+
+    @property
+    def stats(self) -> torch.Tensor:
+        return self.stats_ring[self._stats_slot]
+
+    @property
+    def extras_arr(self) -> torch.Tensor:
+        return self.extras_ring[self.slot]
+
+    def wait_stats(self):
+        """Main stream waits for the side-stream all-reduce + publish of the previous step."""
+        if self._pending is not None:
+            torch.cuda.current_stream().wait_event(self._pending)
+            self._pending = None
+
+    def _finalize_stats(self, allreduce, advance_step_dev: bool):
+        lib, h = self.lib, self.ctx.handle
+        step_dev = nv.ptr(self.step_dev) if advance_step_dev else None
+        if allreduce is None:
+            self._stats_slot = 0
+            st = self.stats_ring[0]
+            nv.check(lib.shifu_collect_stats(h, nv.ptr(st), step_dev, nv.current_stream()))
+            nv.check(lib.shifu_publish_extras_ring(h, nv.ptr(st), nv.ptr(self.extras_ring), EXTRAS_SLOTS,
+                                                   -1 if advance_step_dev else self.slot, nv.ptr(self.step_dev),
+                                                   nv.current_stream()))
+            return
+        self.wait_stats()
+        slot = self._stats_slot = self.slot
+        st = self.stats_ring[slot]
+        nv.check(lib.shifu_collect_stats(h, nv.ptr(st), step_dev, nv.current_stream()))
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            allreduce(st)
+            nv.check(lib.shifu_publish_extras_ring(h, nv.ptr(st), nv.ptr(self.extras_ring), EXTRAS_SLOTS, slot, None,
+                                                   nv.current_stream()))
+            self._pending = torch.cuda.Event()
+            self._pending.record(self._side)
+
+
 class HeightScan:
     """Stand-alone row a5 (``TerrainGymEnv.get_heights``) for user-hook tasks."""
 
@@ -235,7 +298,7 @@ class HeightScan:
         return self.out
 
 
-class A1HotPath:
+class A1HotPath(_StepStats):
     """Fused A1 step. ``root_state`` / ``dof_state`` / ``contact_state`` are the gym's flat tensors."""
 
     def __init__(self, desc: nv.A1Desc, *, root_state, dof_state, contact_state, height_samples,
@@ -279,10 +342,9 @@ class A1HotPath:
         self.measured_heights = torch.zeros(n, 187, **f) if want_measured_heights else None
         self.reset_ids = torch.zeros(n, device=dev, dtype=torch.long)
         self.n_reset = torch.zeros(1, device=dev, dtype=torch.int32)
-        self.stats = torch.zeros(nv.NUM_STATS, device=dev, dtype=torch.double)
-        self.extras_arr = torch.zeros(nv.NUM_STATS, **f)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.long)
         self.step_counter = 0
+        self._init_stats(dev)
         self.carry_body_frame = carry_body_frame
         self._io = None
         nv.check(self.lib.shifu_set_height_map(self.ctx.handle, nv.ptr(self.height_samples),
@@ -331,6 +393,7 @@ class A1HotPath:
         """Row a2 (+a1 when ``raw_actions`` is given: env.actions = clip(0.5*a, +-1) is produced too)."""
         s = nv.current_stream()
         if raw_actions is not None:
+            self.wait_stats()
             nv.check(self.lib.shifu_pd_torque(self.ctx.handle, nv.ptr(raw_actions), nv.ptr(self.actions),
                                               nv.ptr(self.dof_state), nv.ptr(self.torques), s))
         else:
@@ -362,35 +425,24 @@ class A1HotPath:
         nv.check(self.lib.shifu_compact_reset_ids(self.ctx.handle, nv.ptr(self.reset_buf), self.n,
                                                   nv.ptr(self.reset_ids), nv.ptr(self.n_reset), nv.current_stream()))
 
-    def collect_stats(self, advance_step_dev: bool = False):
-        nv.check(self.lib.shifu_collect_stats(self.ctx.handle, nv.ptr(self.stats),
-                                              nv.ptr(self.step_dev) if advance_step_dev else None,
-                                              nv.current_stream()))
-
-    def publish_extras(self):
-        nv.check(self.lib.shifu_publish_extras(self.ctx.handle, nv.ptr(self.stats), nv.ptr(self.extras_arr),
-                                               nv.current_stream()))
-
     def reset_idx(self, env_ids: Optional[torch.Tensor], allreduce=None):
-        """Rows a9-a11 stand-alone (``A1Conditional.reset_idx``); ``None`` = all envs."""
+        """Rows a9-a11 stand-alone (``A1Conditional.reset_idx``); ``None`` = all envs.  In a sharded
+        run every rank must call it (possibly with no ids): the statistics all-reduce is collective."""
         n_ids = self.n if env_ids is None else int(env_ids.numel())
         if env_ids is not None:
             env_ids = env_ids.to(self.device, torch.long).contiguous()
+        self.wait_stats()
         nv.check(self.lib.shifu_a1_reset_idx(self.ctx.handle, C.byref(self.io(False)), nv.ptr(env_ids), n_ids,
                                              nv.current_stream()))
-        if n_ids > 0:                       # log_info runs inside reset_idx (env.py:124-130)
-            self.collect_stats()
-            if allreduce is not None:
-                allreduce(self.stats)
-            self.publish_extras()
+        if n_ids > 0 and self.carry_body_frame:
+            self.body_frame()               # the carried velocities follow the rewritten root rows (robot.py:222-229)
+        if n_ids > 0 or allreduce is not None:      # log_info runs inside reset_idx (env.py:124-130)
+            self._finalize_stats(allreduce, False)
 
     def finalize(self, allreduce=None, advance_step_dev: bool = False):
-        """compaction + stats -> (optional all-reduce over ranks) -> extras."""
+        """compaction + stats -> (optional all-reduce over ranks, on a side stream) -> extras."""
         self.compact()
-        self.collect_stats(advance_step_dev)
-        if allreduce is not None:
-            allreduce(self.stats)
-        self.publish_extras()
+        self._finalize_stats(allreduce, advance_step_dev)
 
     # -- the whole control step without a simulator in between (bench / graph capture) ------
     def step_resident(self, raw_actions: torch.Tensor, decimation: int = 4, use_step_dev: bool = False,
@@ -406,9 +458,11 @@ class A1HotPath:
         self.finalize(allreduce, advance_step_dev=use_step_dev)
 
     def extras(self) -> Dict:
-        """``extras`` dict of 0-dim views (env.py:124-130, a1_conditional.py:126-129)."""
-        ep = {k: self.extras_arr[i] for i, k in enumerate(self.terms)}
-        ep["terrain_levels"] = self.extras_arr[nv.STAT_LEVEL_SUM]
+        """``extras`` of the last finalised step: a fresh dict of 0-dim views into that step's own slot
+        of the ring (env.py:124-130, a1_conditional.py:126-129)."""
+        arr = self.extras_arr
+        ep = {k: arr[i] for i, k in enumerate(self.terms)}
+        ep["terrain_levels"] = arr[nv.STAT_LEVEL_SUM]
         return {"episode": ep, "time_outs": self.time_out_buf}
 
     def reset_id_list(self) -> torch.Tensor:
@@ -447,7 +501,7 @@ def abb_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
     return d
 
 
-class AbbHotPath:
+class AbbHotPath(_StepStats):
     def __init__(self, desc: nv.AbbDesc, *, root_state, body_state, dof_state,
                  terms: Sequence[str] = tuple(ABB_TERM_CODES)):
         dev = root_state.device
@@ -468,10 +522,9 @@ class AbbHotPath:
         self.success_buf = torch.zeros(n, device=dev, dtype=torch.bool)
         self.reset_ids = torch.zeros(n, device=dev, dtype=torch.long)
         self.n_reset = torch.zeros(1, device=dev, dtype=torch.int32)
-        self.stats = torch.zeros(nv.NUM_STATS, device=dev, dtype=torch.double)
-        self.extras_arr = torch.zeros(nv.NUM_STATS, **f)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.long)
         self.step_counter = 0
+        self._init_stats(dev)
         self._io = None
 
     def io(self, use_step_dev: bool = False) -> nv.AbbStepIO:
@@ -494,22 +547,30 @@ class AbbHotPath:
         nv.check(self.lib.shifu_abb_post_physics(self.ctx.handle, C.byref(self.io(use_step_dev)), nv.current_stream()))
 
     def finalize(self, allreduce=None, advance_step_dev: bool = False):
-        s = nv.current_stream()
         nv.check(self.lib.shifu_compact_reset_ids(self.ctx.handle, nv.ptr(self.reset_buf), self.n,
-                                                  nv.ptr(self.reset_ids), nv.ptr(self.n_reset), s))
-        nv.check(self.lib.shifu_collect_stats(self.ctx.handle, nv.ptr(self.stats),
-                                              nv.ptr(self.step_dev) if advance_step_dev else None, s))
-        if allreduce is not None:
-            allreduce(self.stats)
-        nv.check(self.lib.shifu_publish_extras(self.ctx.handle, nv.ptr(self.stats), nv.ptr(self.extras_arr), s))
+                                                  nv.ptr(self.reset_ids), nv.ptr(self.n_reset), nv.current_stream()))
+        self._finalize_stats(allreduce, advance_step_dev)
+
+    def reset_idx(self, env_ids: Optional[torch.Tensor], allreduce=None):
+        """``ShifuVecEnv.reset_idx(env_ids)`` of the push-box scene stand-alone (env.py:114-130 with the
+        random cube / goal poses of a_prior_stage.py:39-51); ``None`` = all envs."""
+        n_ids = self.n if env_ids is None else int(env_ids.numel())
+        if env_ids is not None:
+            env_ids = env_ids.to(self.device, torch.long).contiguous()
+        self.wait_stats()
+        nv.check(self.lib.shifu_abb_reset_idx(self.ctx.handle, C.byref(self.io(False)), nv.ptr(env_ids), n_ids,
+                                              nv.current_stream()))
+        if n_ids > 0 or allreduce is not None:
+            self._finalize_stats(allreduce, False)
 
     def step_resident(self, use_step_dev: bool = False, allreduce=None):
         self.post_physics(use_step_dev)
         self.finalize(allreduce, advance_step_dev=use_step_dev)
 
     def extras(self) -> Dict:
-        ep = {k: self.extras_arr[i] for i, k in enumerate(self.terms)}
-        ep["success_rate"] = self.extras_arr[nv.STAT_SUCCESS]
+        arr = self.extras_arr
+        ep = {k: arr[i] for i, k in enumerate(self.terms)}
+        ep["success_rate"] = arr[nv.STAT_SUCCESS]
         return {"episode": ep, "time_outs": self.time_out_buf}
 
     def reset_id_list(self) -> torch.Tensor:

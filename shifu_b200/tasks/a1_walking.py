@@ -221,6 +221,7 @@ class A1Conditional(ShifuVecEnv):
         hp.post_physics()
         hp.finalize(self.stats_allreduce)
         self._push_resets_to_sim()
+        self.extras.update(hp.extras())            # this step's own slot of the extras ring (fresh inner dict)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def reset(self):
@@ -235,6 +236,7 @@ class A1Conditional(ShifuVecEnv):
             self.hot.step_counter = self.common_step_counter
             self.hot.reset_idx(env_ids, self.stats_allreduce)
             self._push_resets_to_sim(torch.arange(self.num_envs, device=self.device) if env_ids is None else env_ids)
+            self.extras.update(self.hot.extras())
             return
         if self.cfg.terrain.curriculum:
             self.update_terrain_curriculum(env_ids)

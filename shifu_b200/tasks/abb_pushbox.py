@@ -202,12 +202,32 @@ class AbbPushBox(ShifuVecEnv):
         self.hot.step_counter = self.common_step_counter - 1
         self.hot.post_physics()
         self.hot.finalize(self.stats_allreduce)
-        if getattr(self.isg_env.gym, "needs_indexed_resets", True):
-            ids = self.hot.reset_id_list()
-            if len(ids):
-                self.robot.push_dof_reset(ids)
-                self.isg_env.push_root_reset(ids)
+        self._push_resets_to_sim()
+        self.extras.update(self.hot.extras())      # this step's own slot of the extras ring (fresh inner dict)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _push_resets_to_sim(self, env_ids=None):
+        """Indexed setters of the simulator for the rows the kernel rewrote (isaac_gym.py:70-73)."""
+        if not getattr(self.isg_env.gym, "needs_indexed_resets", True):
+            return
+        ids = self.hot.reset_id_list() if env_ids is None else env_ids
+        if len(ids):
+            self.robot.push_dof_reset(ids)
+            self.isg_env.push_root_reset(ids)
+
+    def reset(self):                                                             # env.py:108-112
+        self.reset_idx(None)
+        obs, pri, *_ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return obs, pri
+
+    def reset_idx(self, env_ids):
+        """env.py:114-130 for the 4-actor scene in one launch (``shifu_abb_reset_idx``): default robot /
+        table poses, Philox-drawn cube and goal poses (a_prior_stage.py:39-51), episode bookkeeping and
+        the logged means — ``extras`` keeps pointing at the hot path's ring, never a detached dict."""
+        self.hot.step_counter = self.common_step_counter
+        self.hot.reset_idx(env_ids, self.stats_allreduce)
+        self._push_resets_to_sim(torch.arange(self.num_envs, device=self.device) if env_ids is None else env_ids)
+        self.extras.update(self.hot.extras())
 
     # hooks: the names feed the reward-term registry (a_prior_stage.py:112-127)
     def build_reward_functions(self):

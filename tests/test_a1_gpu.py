@@ -279,3 +279,101 @@ def test_full_size_properties_1m():
     # a second step with no new simulator state is deterministic (same ids)
     n1 = int(hp.n_reset.item())
     assert n1 > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# Parity at the benchmarked sizes and instantiations (the oracle comparison stopped at
+# 38 407 envs and never saw carry=True / no measured_heights or a non-zero env_offset on CUDA)
+# ---------------------------------------------------------------------------------------------
+
+def _oracle_vs_cuda_sharded(n, shards, steps, *, carry, want_heights, seed=91):
+    """CUDA run over n envs against the CPU oracle run shard by shard (contiguous env ranges with
+    their env_offset, so the oracle's memory stays bounded at 1 Mi envs)."""
+    from oracle import shifu_oracle as so
+    hs, origins, _, _ = _terrain(64)
+    world = util.world_state(n, seed, steps, origins)
+    types, levels0, ep0, cmd0, env_origins, snaps, root0 = world
+    hp = util.world_shard_cuda(world, slice(0, n), hs, origins, carry=carry, want_heights=want_heights)
+    got = []
+    for t in range(1, steps + 1):
+        util.cuda_a1_step(hp, snaps[t], snaps[t].actions)
+        got.append(util.cuda_a1_outputs(hp))
+    m = n // shards
+    skip = {"base_lin_vel", "base_ang_vel", "projected_gravity"} if carry else set()
+    skip |= {k for k in got[0] if k.startswith("extras/")} | {"reset_ids"}    # whole-world means / ids: below
+    for s_ in range(shards):
+        sl = slice(s_ * m, (s_ + 1) * m)
+        p, st = util.make_oracle_a1(m, hs, origins, types[sl], env_origins[sl], env_offset=s_ * m)
+        st.ep_len[:] = ep0[sl]
+        st.command[:] = cmd0[sl]
+        st.terrain_levels[:] = levels0[sl]
+        st.root_state[:] = root0[sl]
+        for t in range(1, steps + 1):
+            so.a1_step(p, st, snaps[t].actions[sl], util.slice_snap(snaps[t], sl))
+            want = util.oracle_a1_outputs(st)
+            part = {k: (v[sl] if v.shape[:1] == (n,) else v) for k, v in got[t - 1].items()}
+            part["dof_state"] = got[t - 1]["dof_state"].reshape(n, 12, 2)[sl].reshape(-1, 2)
+            util.compare_a1(part, want, f"n{n}/shard{s_}/s{t}", skip=skip)
+            ids = got[t - 1]["reset_ids"]
+            local = ids[(ids >= s_ * m) & (ids < (s_ + 1) * m)] - s_ * m
+            assert np.array_equal(local, st.reset_ids.numpy()), f"reset ids differ: shard {s_} step {t}"
+    return hp, got, world
+
+
+@pytest.mark.parametrize("n,shards,carry,want_heights", [
+    (65536, 1, True, False),           # the benchmarked instantiation (carry, no measured_heights)
+    (262144, 2, True, False),
+    (262144, 2, False, True),
+    (1 << 20, 8, True, False),         # BASELINE configs[2] size, benchmarked instantiation
+])
+def test_oracle_parity_benchmark_sizes(n, shards, carry, want_heights):
+    _oracle_vs_cuda_sharded(n, shards, 2, carry=carry, want_heights=want_heights)
+
+
+def test_env_offset_on_cuda():
+    """Sharded layout on the CUDA path: a shard created with env_offset = r*n draws the Philox
+    samples / terrain types of global envs r*n ..., so (i) the whole world matches the oracle run
+    shard by shard with those offsets and (ii) four CUDA shards of the 4n-env world concatenate to
+    the single 4n-env CUDA run bit for bit."""
+    n, k = 8192, 4
+    whole, got_w, world = _oracle_vs_cuda_sharded(n * k, k, 2, carry=True, want_heights=False, seed=17)
+    hs, origins, _, _ = _terrain(64)
+    snaps = world[5]
+    for r in range(k):
+        sl = slice(r * n, (r + 1) * n)
+        hp = util.world_shard_cuda(world, sl, hs, origins, carry=True, want_heights=False)
+        for t in (1, 2):
+            util.cuda_a1_step(hp, util.slice_snap(snaps[t], sl), snaps[t].actions[sl])
+            got = util.cuda_a1_outputs(hp)
+            for key in ("obs", "rew", "reset", "time_out", "ep_len", "terrain_levels", "command", "root_state",
+                        "env_origins", "history", "rand_force"):
+                w = got_w[t - 1][key]
+                assert np.array_equal(got[key], w[sl]), f"shard {r} step {t}: {key} differs from the 1-process run"
+            ids_w = got_w[t - 1]["reset_ids"]
+            assert np.array_equal(got["reset_ids"] + r * n, ids_w[(ids_w >= r * n) & (ids_w < (r + 1) * n)])
+
+
+def test_two_rank_nccl_matches_one_rank(tmp_path):
+    """2 ranks over NCCL (skipped on a 1-GPU box): concatenated obs / reset ids / levels and the
+    all-reduced extras equal the 1-rank run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "ranks"
+    out.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(root, "tests", "nccl_two_rank_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    one = np.load(out / "world1.npz")
+    parts = [np.load(out / f"rank{i}.npz") for i in range(2)]
+    for key in ("obs", "rew", "reset", "terrain_levels", "ep_len"):
+        assert np.array_equal(np.concatenate([p[key] for p in parts]), one[key]), key
+    n = parts[0]["obs"].shape[0]
+    ids = np.concatenate([p["reset_ids"] + i * n for i, p in enumerate(parts)])
+    assert np.array_equal(ids, one["reset_ids"])
+    np.testing.assert_allclose(parts[0]["extras"], one["extras"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(parts[1]["extras"], one["extras"], rtol=1e-5, atol=1e-6)

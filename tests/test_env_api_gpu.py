@@ -155,3 +155,71 @@ def test_no_cpu_fallback():
         hotpath.EnvKernels("cpu", 16)
     with pytest.raises(nv.ShifuNativeError):
         nv.ptr(torch.zeros(4))
+
+
+def test_abb_env_reset_and_reset_idx():
+    """AbbPushBox.reset() / reset_idx() — what rsl_rl's OnPolicyRunner and the
+    reference's run_policy call first (policy_runner.py:22,33; env.py:108-130).  The reset state is
+    compared with the oracle's abb_reset_idx driven by the same Philox streams."""
+    from oracle import shifu_oracle as so
+    _install()
+    from shifu_b200.sim.synthetic import AbbReplay, abb_snapshot
+    from shifu_b200.tasks.abb_pushbox import AbbPushBox, PriorStageEnvConfig
+    n = 1000
+    cfg = PriorStageEnvConfig()
+    cfg.num_envs, cfg.device = n, "cuda:0"
+    env = AbbPushBox(cfg, rng_seed=99)
+    p = so.AbbParams(n=n, rng_seed=99)
+    st = so.abb_new_state(p)
+    st.success = torch.zeros(n, dtype=torch.bool)          # the env's success_buf before the first step
+    # --- reset(): reset_idx(all) at step counter 0 ...
+    extras_id = id(env.extras)
+    env.reset_idx(None)
+    so.abb_reset_idx(p, st, torch.arange(n))
+    util.assert_close("root after reset_idx", env.isg_env.root_state.cpu().numpy(), st.root_state.numpy(), exact=False)
+    util.assert_close("dof after reset_idx", env.isg_env.dof_state.cpu().numpy(), st.dof_state.numpy(), exact=True)
+    cube = env.isg_env.root_state.view(n, 4, 13)[:, 2]
+    goal = env.isg_env.root_state.view(n, 4, 13)[:, 3]
+    assert float((cube[:, :2] - goal[:, :2]).norm(dim=1).min()) > 0.0     # not the default (coincident) poses
+    assert float(cube[:, :2].abs().max()) <= 0.1 + 1e-6 and float(env.episode_length_buf.abs().sum()) == 0
+    assert id(env.extras) == extras_id and set(env.extras["episode"]) == {"reward_reaching", "reward_success",
+                                                                          "success_rate"}
+    # ... then a zero-action step; the full reset() is what a runner calls
+    env.isg_env.sim.provider = AbbReplay(3, n)
+    obs, priv = env.reset()
+    assert obs.shape == (n, 6) and priv is None and torch.isfinite(obs).all()
+    # --- reset_idx(ids) mid-run: only those envs change, their episode sums are logged and zeroed
+    env.isg_env.sim.provider.enabled = False
+    env.episode_rewards["reward_reaching"].fill_(2.0)
+    before = env.isg_env.root_state.clone()
+    ids = torch.tensor([3, 10, 500], device="cuda")
+    env.reset_idx(ids)
+    keep = torch.ones(n, dtype=torch.bool, device="cuda")
+    keep[ids] = False
+    assert torch.equal(env.isg_env.root_state.view(n, 4, 13)[keep], before.view(n, 4, 13)[keep])
+    assert float(env.episode_rewards["reward_reaching"][ids].abs().sum()) == 0
+    assert abs(float(env.extras["episode"]["reward_reaching"]) - 2.0 / 20.0) < 1e-6      # mean / max_episode_length_s
+    assert int(env.episode_length_buf[ids].abs().sum()) == 0
+
+
+def test_extras_of_each_step_keep_their_own_storage():
+    """rsl_rl appends infos['episode'] every step and reduces the list at the end
+    of the iteration; the reference allocates fresh tensors per resetting step (env.py:124-130)."""
+    from shifu_b200.sim.synthetic import A1Replay
+    z, meta = util.load_golden("a1_small")
+    env = _make_a1(meta["n"], meta["terrain"], fused=True, carry=True)
+    replay = A1Replay(5, meta["n"], lambda: env.isg_env.env_origins, p_base=0.3)
+    env.isg_env.sim.provider = replay
+    env.reset()
+    kept, values = [], []
+    for t in range(1, 9):
+        actions = replay.begin_step(t)
+        _, _, _, dones, extras = env.step(actions.cuda())
+        kept.append(extras["episode"])
+        values.append({k: float(v) for k, v in extras["episode"].items()})
+    assert len({id(d) for d in kept}) == len(kept)
+    ptrs = {d["tracking_lin_vel"].data_ptr() for d in kept}
+    assert len(ptrs) == len(kept), "every step's extras must live in its own slot"
+    for d, v in zip(kept, values):                                  # later steps did not overwrite earlier ones
+        assert {k: float(x) for k, x in d.items()} == v
+    assert len({v["tracking_lin_vel"] for v in values}) > 1

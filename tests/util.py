@@ -155,3 +155,45 @@ def compare_a1(got: Dict, want: Dict, tag: str, skip=()):
         if k in skip or k not in got:
             continue
         assert_close(f"{tag}:{k}", got[k], w, exact=(k in EXACT_KEYS))
+
+
+# ---------------------------------------------------------------------------------------------
+# A world of n_global envs cut into contiguous shards: same global initial state and
+# snapshots whatever the shard layout
+# ---------------------------------------------------------------------------------------------
+
+def slice_snap(snap, sl):
+    return type(snap)(dof=snap.dof[:, sl], root_offset=snap.root_offset[sl], contact=snap.contact[sl],
+                      actions=snap.actions[sl])
+
+
+def world_state(n_global, seed, steps, height_origins):
+    """Global initial state + per-step snapshots (CPU) of a seeded world."""
+    from shifu_b200 import dist as sdist
+    from shifu_b200.sim.synthetic import a1_snapshot
+    origins = height_origins
+    types = sdist.global_terrain_types(0, n_global, n_global, 20).clamp_(max=19)
+    rs = np.random.RandomState(seed)
+    levels0 = torch.from_numpy(rs.randint(0, 6, size=n_global))
+    ep0 = torch.from_numpy(rs.randint(0, 500, size=n_global))
+    cmd0 = torch.from_numpy(rs.uniform(-1, 1, size=(n_global, 3)).astype(np.float32))
+    env_origins = origins[levels0, types]
+    snaps = [a1_snapshot(seed, t, n_global, p_base=0.02, offmap=False) for t in range(steps + 1)]
+    root0 = snaps[0].root_offset.clone()
+    root0[:, :3] += env_origins
+    return types, levels0, ep0, cmd0, env_origins, snaps, root0
+
+
+def world_shard_cuda(world, sl, hs, origins, *, carry, want_heights, device="cuda:0"):
+    """CUDA hot path over the envs `sl` of a world (env_offset = sl.start), seeded like the world."""
+    types, levels0, ep0, cmd0, env_origins, snaps, root0 = world
+    n = sl.stop - sl.start
+    hp = make_cuda_a1(n, hs, origins, types[sl], env_origins[sl], carry=carry, want_measured_heights=want_heights,
+                      env_offset=sl.start, device=device)
+    hp.ep_len.copy_(ep0[sl])
+    hp.command.copy_(cmd0[sl])
+    hp.terrain_levels.copy_(levels0[sl])
+    hp.sync_level_sum()
+    hp.root_state.copy_(root0[sl].to(hp.device))     # S_prev of the first step's body-frame velocities (D7)
+    hp.body_frame()
+    return hp
