@@ -59,7 +59,15 @@ enum ShifuRewardTerm {
   SHIFU_REW_TORQUES = 5,          /* p0*|tau|^2                                 :191-192 */
   SHIFU_REW_ABB_REACHING = 6,     /* [|ee-cube|<p0] * exp(-|goal-cube|^2 / p1)  a_prior_stage.py:118-123 */
   SHIFU_REW_ABB_SUCCESS = 7,      /* p0*[|goal-cube| < p1]                      :125-131 */
-  SHIFU_REW_COUNT = 8
+  /* legged_gym-style terms for user task lists (shifu/gym/env.py:160-185 accepts any
+   * list; the buffers of a1_conditional.py:100-103 / robot.py:215 hint at them) */
+  SHIFU_REW_LIN_VEL_Z = 8,        /* p0*v_z^2                         torch.square(base_lin_vel[:, 2]) */
+  SHIFU_REW_ANG_VEL_XY = 9,       /* p0*|w_xy|^2                      sum(square(base_ang_vel[:, :2])) */
+  SHIFU_REW_ORIENTATION = 10,     /* p0*|g_xy|^2                      sum(square(projected_gravity[:, :2])), robot.py:215 */
+  SHIFU_REW_DOF_VEL = 11,         /* p0*|qd|^2                        sum(square(dof_vel)) */
+  SHIFU_REW_ACTION_RATE = 12,     /* p0*|a_{t-1} - a_t|^2             sum(square(actions_recorder.get_last(0) - actions)) */
+  SHIFU_REW_BASE_HEIGHT = 13,     /* p0*(z - p1)^2                    square(base_pose[:, 2] - p1) */
+  SHIFU_REW_COUNT = 14
 };
 
 /* Index of each statistic in the stats vector (double[SHIFU_NUM_STATS]) that
@@ -254,6 +262,12 @@ int shifu_get_heights(ShifuCtx* ctx, const float* root_state, float* measured_he
 /* ---- rows a5-a7, a9-a14: the fused A1 post-physics step ------------------------------------
  * ShifuVecEnv.post_step (env.py:93-106) + obs clip (env.py:90) with the A1 task hooks. */
 int shifu_a1_post_physics(ShifuCtx* ctx, const ShifuA1StepIO* io, void* stream);
+
+/* ---- row a7 stand-alone / N1 self-check: the listed reward terms on the CURRENT tensors ------
+ * terms_out[k*N + e] = value of term k of the descriptor for env e (no accumulation, no writes to
+ * the env state).  The host-side term compiler calls the user's Python hook on the same tensors and
+ * refuses to fuse when the two disagree (shifu/gym/env.py:180-185). */
+int shifu_a1_eval_terms(ShifuCtx* ctx, const ShifuA1StepIO* io, float* terms_out, void* stream);
 
 /* ---- rows a9-a11 stand-alone: A1Conditional.reset_idx(env_ids) ------------------------------
  * (a1_conditional.py:116-120; used by ShifuVecEnv.reset, env.py:108-112, and by user code).

@@ -17,6 +17,7 @@ ABI_VERSION = 1
 # enum ShifuRewardTerm
 REW_TRACKING_LIN_VEL, REW_TRACKING_ANG_VEL, REW_STABILIZING_BASE, REW_SMOOTHING_ACTION = 0, 1, 2, 3
 REW_LEG_COLLISION, REW_TORQUES, REW_ABB_REACHING, REW_ABB_SUCCESS = 4, 5, 6, 7
+REW_LIN_VEL_Z, REW_ANG_VEL_XY, REW_ORIENTATION, REW_DOF_VEL, REW_ACTION_RATE, REW_BASE_HEIGHT = 8, 9, 10, 11, 12, 13
 STAT_TERM0, STAT_NRESET, STAT_LEVEL_SUM, STAT_SUCCESS, STAT_NENVS = 0, 8, 9, 10, 11
 
 E_NULL, E_RANGE, E_STATE, E_NODEVICE, E_ALIGN = -1, -2, -3, -4, -5
@@ -128,6 +129,7 @@ SIGNATURES = {
     "shifu_body_frame": [_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP],
     "shifu_get_heights": [_VP, _VP, _VP, _VP, _VP],
     "shifu_a1_post_physics": [_VP, C.POINTER(A1StepIO), _VP],
+    "shifu_a1_eval_terms": [_VP, C.POINTER(A1StepIO), _VP, _VP],
     "shifu_abb_post_physics": [_VP, C.POINTER(AbbStepIO), _VP],
     "shifu_compact_reset_ids": [_VP, _VP, _I32, _VP, _VP, _VP],
     "shifu_history_add": [_VP, _VP, _VP, _I32, _I32, _I32, _VP],

@@ -62,8 +62,46 @@ __device__ __forceinline__ void store_span(float* __restrict__ dst, const float*
 
 // One reward term for env e (lane = env).  a1_conditional.py:162-192; every op rounds like the
 // aten elementwise op it stands for.
-__device__ __noinline__ float a1_eval_term(int code, float p0, float p1, const A1K& k, const A1Smem& s, int e) {
+// Terms 8-13 (legged_gym-style, see enum ShifuRewardTerm): pg = this step's projected gravity row.
+__device__ __forceinline__ float a1_extra_term(int code, float p0, float p1, const float* lin, const float* ang,
+                                               const float* pg, const float* dof_row, const float* hist_row,
+                                               const float* act_row, float base_z) {
+  switch (code) {
+    case SHIFU_REW_LIN_VEL_Z:
+      return mul_rn(p0, mul_rn(lin[2], lin[2]));
+    case SHIFU_REW_ANG_VEL_XY:
+      return mul_rn(p0, add_rn(mul_rn(ang[0], ang[0]), mul_rn(ang[1], ang[1])));
+    case SHIFU_REW_ORIENTATION:
+      return mul_rn(p0, add_rn(mul_rn(pg[0], pg[0]), mul_rn(pg[1], pg[1])));
+    case SHIFU_REW_DOF_VEL: {
+      float acc = 0.0f;
+#pragma unroll
+      for (int d = 0; d < A1_DOF; ++d) acc = add_rn(acc, mul_rn(dof_row[2 * d + 1], dof_row[2 * d + 1]));
+      return mul_rn(p0, acc);
+    }
+    case SHIFU_REW_ACTION_RATE: {
+      float acc = 0.0f;
+#pragma unroll
+      for (int d = 0; d < A1_DOF; ++d) {
+        const float df = sub_rn(hist_row[d * A1_HIST], act_row[d]);
+        acc = add_rn(acc, mul_rn(df, df));
+      }
+      return mul_rn(p0, acc);
+    }
+    case SHIFU_REW_BASE_HEIGHT: {
+      const float df = sub_rn(base_z, p1);
+      return mul_rn(p0, mul_rn(df, df));
+    }
+    default:
+      return 0.0f;
+  }
+}
+
+__device__ __noinline__ float a1_eval_term(int code, float p0, float p1, const A1K& k, const A1Smem& s, int e,
+                                           const float* pg) {
   const float* cla = s.cla[e];
+  if (code >= SHIFU_REW_LIN_VEL_Z)
+    return a1_extra_term(code, p0, p1, cla + 3, cla + 6, pg, s.dof[e], s.hist[e], s.act[e], s.root[e][2]);
   switch (code) {
     case SHIFU_REW_TRACKING_LIN_VEL: {
       const float dx = sub_rn(cla[0], cla[3]), dy = sub_rn(cla[1], cla[4]);
@@ -168,7 +206,8 @@ a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ Sh
     if (lane_env) {
 #pragma unroll 1
       for (int j = warp; j < k.n_terms; j += A1_THREADS / 32)
-        s.rterm[j][lane] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane);
+        s.rterm[j][lane] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane,
+                                        io.projected_gravity + (long long)ge * 3);
       if (warp == 0) {                                                  // a1_conditional.py:146-148
         const float* fb = &s.contact[lane][k.base_body * 3];
         contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
@@ -313,6 +352,41 @@ a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ Sh
       }
     }
     __syncthreads();   // shared memory is reused by the next tile of a grid-stride CTA
+  }
+}
+
+// Row a7 stand-alone (shifu_a1_eval_terms): the descriptor's term list on the current tensors, one
+// CTA per 32 envs with the rows staged like phase A of the fused kernel; writes nothing but out.
+__global__ void __launch_bounds__(A1_THREADS)
+a1_eval_terms_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io, float* __restrict__ out) {
+  __shared__ __align__(16) A1Smem s;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int e0 = blockIdx.x * A1_TILE; e0 < k.n; e0 += gridDim.x * A1_TILE) {
+    const int ne = min(A1_TILE, k.n - e0);
+    const int ge = e0 + lane;
+    __syncthreads();
+    for (int i = t; i < ne * 13; i += A1_THREADS) {
+      const int e = i / 13, c = i % 13;
+      s.root[e][c] = io.root_state[((long long)(e0 + e) * k.root_stride + k.root_offset) * 13 + c];
+    }
+    load_span(&s.dof[0][0], io.dof_state + (long long)e0 * (A1_DOF * 2), ne * A1_DOF * 2, t, A1_THREADS);
+    load_span(&s.contact[0][0], io.contact_state + (long long)e0 * (A1_BODIES * 3), ne * A1_BODIES * 3, t, A1_THREADS);
+    load_span(&s.hist[0][0], io.history + (long long)e0 * (A1_DOF * A1_HIST), ne * A1_DOF * A1_HIST, t, A1_THREADS);
+    load_span(&s.tau[0][0], io.torques + (long long)e0 * A1_DOF, ne * A1_DOF, t, A1_THREADS);
+    load_span(&s.act[0][0], io.actions + (long long)e0 * A1_DOF, ne * A1_DOF, t, A1_THREADS);
+    if (warp == 0 && lane < ne) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        s.cla[lane][j] = io.command[ge * 3LL + j];
+        s.cla[lane][3 + j] = io.base_lin_vel[ge * 3LL + j];
+        s.cla[lane][6 + j] = io.base_ang_vel[ge * 3LL + j];
+      }
+    }
+    __syncthreads();
+    if (lane < ne)
+      for (int j = warp; j < k.n_terms; j += A1_THREADS / 32)
+        out[(long long)j * k.n + ge] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane,
+                                                    io.projected_gravity + (long long)ge * 3);
   }
 }
 

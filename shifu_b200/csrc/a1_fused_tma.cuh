@@ -208,10 +208,13 @@ __device__ V3_NOINLINE void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1
 }
 
 // Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
-__device__ V3_NOINLINE float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in, int e) {
+__device__ V3_NOINLINE float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in, int e,
+                                          const float* pg) {
   const float* cmd = in.cla[0][e];
   const float* lin = in.cla[1][e];
   const float* ang = in.cla[2][e];
+  if (code >= SHIFU_REW_LIN_VEL_Z)       // legged_gym-style terms (rare: pg comes straight from global memory)
+    return a1_extra_term(code, p0, p1, lin, ang, pg, in.dof[e], in.hist[e], in.act[e], in.root[e][2]);
   switch (code) {
     case SHIFU_REW_TRACKING_LIN_VEL: {
       const float dx = sub_rn(cmd[0], lin[0]), dy = sub_rn(cmd[1], lin[1]);
@@ -365,7 +368,8 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #ifdef V3_WI_NOB1
         s.rterm[j & 1][q][lane] = 0.0f;
 #else
-        s.rterm[j & 1][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane);
+        s.rterm[j & 1][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane,
+                                               io.projected_gravity + ge * 3);
 #endif
       }
       V3_TICK(warp == 0 ? 2 : 6);

@@ -113,7 +113,8 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
     if (d.leg_bodies[i] < 0 || d.leg_bodies[i] >= A1_BODIES) return fail(SHIFU_E_RANGE, "leg_bodies[%d] out of range", i);
   if (d.num_reward_terms < 0 || d.num_reward_terms > SHIFU_MAX_REWARD_TERMS) return fail(SHIFU_E_RANGE, "num_reward_terms out of range");
   for (int i = 0; i < d.num_reward_terms; ++i)
-    if (d.reward_terms[i] < 0 || d.reward_terms[i] > SHIFU_REW_TORQUES)
+    if (d.reward_terms[i] < 0 || d.reward_terms[i] >= SHIFU_REW_COUNT ||
+        d.reward_terms[i] == SHIFU_REW_ABB_REACHING || d.reward_terms[i] == SHIFU_REW_ABB_SUCCESS)
       return fail(SHIFU_E_RANGE, "reward_terms[%d]=%d is not an A1 term", i, d.reward_terms[i]);
   if (d.root_stride < 1 || d.root_offset < 0 || d.root_offset >= d.root_stride) return fail(SHIFU_E_RANGE, "root_stride/root_offset invalid");
   if (!(d.horizontal_scale > 0.f) || d.max_terrain_level < 1 || d.num_terrain_types < 1) return fail(SHIFU_E_RANGE, "terrain constants invalid");
@@ -159,10 +160,10 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   k.contact_thr_sq = sqrt_threshold(d.contact_term_force);
   // Split of the term list over the two B warps of the pipelined kernel: longest-processing-time
   // greedy on rough per-term instruction counts; warp 0 also carries the yaw normalisation (~60).
-  static const int term_cost[] = {30, 25, 12, 135, 70, 40, 20, 20};
+  static const int term_cost[SHIFU_REW_COUNT] = {30, 25, 12, 135, 70, 40, 20, 20, 8, 10, 10, 40, 60, 8};
   int load[2] = {60, 0}, order[SHIFU_MAX_REWARD_TERMS];
   for (int i = 0; i < k.n_terms; ++i) order[i] = i;
-  auto cost_of = [&](int q) { const int c = k.terms[q]; return (c >= 0 && c < 8) ? term_cost[c] : 40; };
+  auto cost_of = [&](int q) { const int c = k.terms[q]; return (c >= 0 && c < SHIFU_REW_COUNT) ? term_cost[c] : 40; };
   for (int i = 0; i < k.n_terms; ++i)
     for (int j = i + 1; j < k.n_terms; ++j)
       if (cost_of(order[j]) > cost_of(order[i])) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
@@ -385,6 +386,19 @@ extern "C" int shifu_get_heights(ShifuCtx* c, const float* root, float* mh, int3
   const int tiles = (c->a1.num_envs + A1_TILE - 1) / A1_TILE;
   const int cap = c->sm_count * 8;
   get_heights_kernel<<<tiles < cap ? tiles : cap, A1_THREADS, 0, S(stream)>>>(c->a1k, root, mh, cell_idx);
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_a1_eval_terms(ShifuCtx* c, const ShifuA1StepIO* io, float* out, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(io); REQUIRE_PTR(out);
+  if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_a1_eval_terms needs an A1 ctx");
+  REQUIRE_PTR(io->root_state); REQUIRE_PTR(io->dof_state); REQUIRE_PTR(io->contact_state); REQUIRE_PTR(io->actions);
+  REQUIRE_PTR(io->torques); REQUIRE_PTR(io->history); REQUIRE_PTR(io->command); REQUIRE_PTR(io->base_lin_vel);
+  REQUIRE_PTR(io->base_ang_vel); REQUIRE_PTR(io->projected_gravity);
+  const int tiles = (c->a1.num_envs + A1_TILE - 1) / A1_TILE;
+  const int cap = c->sm_count * 8;
+  a1_eval_terms_kernel<<<tiles < cap ? tiles : cap, A1_THREADS, 0, S(stream)>>>(c->a1k, *io, out);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }

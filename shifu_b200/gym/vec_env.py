@@ -31,6 +31,10 @@ from shifu_b200.utils.history import HistoryRecorder
 
 
 class ShifuVecEnv(VecEnv):
+    #: try to replace the Python hooks by a fused kernel on the first reset()/step() (see autofuse.py);
+    #: set to False (class or instance) to keep the hooks as eager torch code
+    auto_fuse = True
+
     # ------------------------------------------------------------------ construction (env.py:19-63)
     def __init__(self, cfg: BaseEnvConfig, env_offset: int = 0, num_envs_global: Optional[int] = None):
         self.cfg = cfg
@@ -49,6 +53,9 @@ class ShifuVecEnv(VecEnv):
         self.common_step_counter = 0
         self.stats_allreduce: Optional[Callable] = None    # sums a tensor over ranks (sharded runs)
         self.extras: Dict = {}
+        self.fusion_report = "not attempted"
+        self._fusion = None            # (recipe, hot path, step fn, reset_idx fn) once fused
+        self._fusion_tried = False
         self._allocate()
         self.reward_functions: List[Callable] = self.build_reward_functions()
         self._prepare_reward_functions()
@@ -105,9 +112,33 @@ class ShifuVecEnv(VecEnv):
     def episode_log(self, env_ids) -> Optional[Dict]:
         return None
 
+    # ------------------------------------------------------------------ automatic fusion
+    def _maybe_fuse(self):
+        """First reset()/step(): replace the hooks by a fused kernel when they provably are what the kernel
+        computes (autofuse.py).  Tasks that manage their own fusion (shifu_b200.tasks) set ``hot``."""
+        if self._fusion_tried:
+            return self._fusion
+        self._fusion_tried = True
+        if not self.auto_fuse or getattr(self, "hot", None) is not None or not hasattr(self, "robot"):
+            return None
+        from shifu_b200.gym import autofuse
+        self._fusion = autofuse.try_fuse(self, rng_seed=getattr(self.cfg, "rng_seed", 0x5EED),
+                                         carry_body_frame=getattr(self.cfg, "carry_body_frame", True))
+        if self._fusion is not None:
+            recipe, hp, step_fn, reset_fn = self._fusion
+            self.hot = hp
+            # a subclass reset_idx (curriculum + command sampling in torch) is part of what got fused
+            self.reset_idx = lambda env_ids: reset_fn(self, hp, env_ids)
+            if recipe == "a1":
+                hp.body_frame()
+        return self._fusion
+
     # ------------------------------------------------------------------ orchestration, user-hook mode
     def step(self, actions: torch.Tensor):
         assert self.isg_env.robot, "add robot before step"
+        fusion = self._maybe_fuse()
+        if fusion is not None:
+            return fusion[2](self, fusion[1], actions)
         kernels = self.isg_env.kernels()
         kernels.clip(actions, self.clip_actions, out=self.actions)               # env.py:87
         self.isg_env.step(self.actions)
@@ -134,6 +165,7 @@ class ShifuVecEnv(VecEnv):
             self.rew_buf += value
 
     def reset(self):
+        self._maybe_fuse()
         everyone = torch.arange(self.num_envs, device=self.device)
         self.reset_idx(everyone)
         idle = torch.zeros(self.num_envs, self.num_actions, device=self.device, requires_grad=False)

@@ -22,7 +22,12 @@ A1_TERM_CODES = {
     "tracking_lin_vel": nv.REW_TRACKING_LIN_VEL, "tracking_ang_vel": nv.REW_TRACKING_ANG_VEL,
     "stabilizing_base": nv.REW_STABILIZING_BASE, "smoothing_action": nv.REW_SMOOTHING_ACTION,
     "leg_collision": nv.REW_LEG_COLLISION, "torques_penalize": nv.REW_TORQUES,
+    # legged_gym-style additions; constants come from shifu_b200.terms (fitted from the hook)
+    "lin_vel_z": nv.REW_LIN_VEL_Z, "ang_vel_xy": nv.REW_ANG_VEL_XY, "orientation": nv.REW_ORIENTATION,
+    "dof_vel": nv.REW_DOF_VEL, "action_rate": nv.REW_ACTION_RATE, "base_height": nv.REW_BASE_HEIGHT,
 }
+A1_DEFAULT_TERMS = ("tracking_lin_vel", "tracking_ang_vel", "stabilizing_base", "smoothing_action", "leg_collision",
+                    "torques_penalize")              # build_reward_functions() of a1_conditional.py:152-160
 # literal constants of the reward methods, examples/a1_conditional/a1_conditional.py:162-192
 A1_TERM_PARAMS = {
     "tracking_lin_vel": (1.0, 0.25), "tracking_ang_vel": (0.5, 0.25), "stabilizing_base": (-2.0, -0.005),
@@ -42,14 +47,20 @@ def compile_reward_terms(names: Sequence[str], codes: Dict[str, int], params: Di
         raise ValueError(f"at most {nv.MAX_TERMS} fused reward terms are supported")
     out = []
     for n in names:
+        if isinstance(n, (tuple, list)):          # already compiled: (name, code, p0, p1) from shifu_b200.terms
+            out.append((int(n[1]), float(n[2]), float(n[3])))
+            continue
         if n not in codes:
             raise KeyError(f"reward term {n!r} has no fused implementation; known: {sorted(codes)}")
+        if n not in params:
+            raise KeyError(f"reward term {n!r} needs its constants: pass term_params or compile the list with "
+                           "shifu_b200.terms.compile_a1_terms")
         out.append((codes[n], float(params[n][0]), float(params[n][1])))
     return out
 
 
 def a1_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
-            terms: Sequence[str] = tuple(A1_TERM_CODES), term_params: Optional[Dict[str, tuple]] = None,
+            terms: Sequence[str] = A1_DEFAULT_TERMS, term_params: Optional[Dict[str, tuple]] = None,
             q0=(0.1, 0.8, -1.5, 0.1, 0.8, -1.5, -0.1, 0.8, -1.5, -0.1, 0.8, -1.5),
             kp=(20.,) * 12, kd=(.5,) * 12, torque_limit=(20., 55., 55.) * 4,
             points_x=(-0.8, -0.7, -0.6, -0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8),
@@ -302,7 +313,7 @@ class A1HotPath(_StepStats):
     """Fused A1 step. ``root_state`` / ``dof_state`` / ``contact_state`` are the gym's flat tensors."""
 
     def __init__(self, desc: nv.A1Desc, *, root_state, dof_state, contact_state, height_samples,
-                 terrain_origins, terrain_types, env_origins, terms: Sequence[str] = tuple(A1_TERM_CODES),
+                 terrain_origins, terrain_types, env_origins, terms: Sequence[str] = A1_DEFAULT_TERMS,
                  carry_body_frame: bool = False, want_measured_heights: bool = True):
         dev = root_state.device
         self.device = dev
@@ -384,6 +395,30 @@ class A1HotPath(_StepStats):
     def invalidate_io(self):
         """Call after re-binding any tensor attribute (pointers are cached)."""
         self._io = None
+
+    _ADOPTABLE = ("actions", "torques", "history", "command", "ep_len", "base_lin_vel", "base_ang_vel",
+                  "projected_gravity", "terrain_levels", "dof_targets", "rand_force")
+
+    def adopt(self, **tensors):
+        """Use the caller's existing tensors instead of the ones allocated here (an env built by user
+        code already owns them; its hooks close over them).  Shapes / dtypes must match."""
+        for name, t in tensors.items():
+            if name not in self._ADOPTABLE:
+                raise KeyError(f"{name} cannot be adopted")
+            mine = getattr(self, name)
+            if t.shape != mine.shape or t.dtype != mine.dtype or t.device != mine.device or not t.is_contiguous():
+                raise ValueError(f"{name}: expected contiguous {tuple(mine.shape)} {mine.dtype} on {mine.device}, got "
+                                 f"{tuple(t.shape)} {t.dtype} on {t.device}")
+            setattr(self, name, t)
+        self.invalidate_io()
+        if "terrain_levels" in tensors:
+            self.sync_level_sum()
+
+    def eval_terms(self) -> torch.Tensor:
+        """(num_terms, N): every listed reward term on the current tensors (``shifu_a1_eval_terms``)."""
+        out = torch.empty(len(self.terms), self.n, device=self.device, dtype=torch.float)
+        nv.check(self.lib.shifu_a1_eval_terms(self.ctx.handle, C.byref(self.io(False)), nv.ptr(out), nv.current_stream()))
+        return out
 
     def sync_level_sum(self):
         nv.check(self.lib.shifu_set_level_sum(self.ctx.handle, nv.ptr(self.terrain_levels), nv.current_stream()))
@@ -471,7 +506,7 @@ class A1HotPath(_StepStats):
 
 
 def abb_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
-             terms: Sequence[str] = tuple(ABB_TERM_CODES)) -> nv.AbbDesc:
+             terms: Sequence[str] = tuple(ABB_TERM_CODES), term_params: Optional[Dict[str, tuple]] = None) -> nv.AbbDesc:
     """Constants of ``examples/abb_pushbox_vision`` prior stage (task_config.py:49-91)."""
     d = nv.AbbDesc()
     d.abi_version = nv.ABI_VERSION
@@ -493,7 +528,7 @@ def abb_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
     d.goal_z = 0.1
     d.success_distance = 0.02
     d.max_episode_length, d.max_episode_length_s, d.clip_obs = 200, 20., 10.
-    comp = compile_reward_terms(list(terms), ABB_TERM_CODES, ABB_TERM_PARAMS)
+    comp = compile_reward_terms(list(terms), ABB_TERM_CODES, {**ABB_TERM_PARAMS, **(term_params or {})})
     d.num_reward_terms = len(comp)
     for i, (code, p0, p1) in enumerate(comp):
         d.reward_terms[i] = code

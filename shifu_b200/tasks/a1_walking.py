@@ -132,6 +132,7 @@ class A1Conditional(ShifuVecEnv):
     def __init__(self, cfg, fused: bool = True, carry_body_frame: bool = False, rng_seed: int = 0x5EED,
                  env_offset: int = 0, num_envs_global: int = None):
         super().__init__(cfg, env_offset=env_offset, num_envs_global=num_envs_global)
+        self.auto_fuse = False          # this class wires its own fusion (explicit fused= switch)
         self.fused = fused
         self.rng_seed = rng_seed
         self.robot = A1Robot(A1ActorConfig())

@@ -153,6 +153,7 @@ class AbbPushBox(ShifuVecEnv):
 
     def __init__(self, cfg, rng_seed: int = 0x5EED, env_offset: int = 0):
         super().__init__(cfg, env_offset=env_offset)
+        self.auto_fuse = False          # this class wires its own fusion
         self.rng_seed = rng_seed
         self.robot = AbbRobot(AbbRobotConfig())
         self.table = Box(TableConfig())
