@@ -90,109 +90,141 @@ def _terrain():
     return Terrain(cfg.terrain, 1), cfg
 
 
-def build_a1(n_local, rank, world, device, terrain=None, seed=1234, carry=True, want_heights=False):
-    """Resident synthetic state for n_local envs on `device` (global ids rank*n_local ...)."""
+def build_env(n_local, rank, world, device, seed=1234, store_heights=False, use_graph=True):
+    """The product's class API (shifu_b200.tasks.a1_walking.A1Conditional — the counterpart of the
+    reference's example class — over ShifuVecEnv / TerrainGymEnv / LeggedRobot) on the stand-in
+    simulator with synthetic state RESIDENT in HBM (no snapshot provider: what the hot path sees between
+    two PhysX steps).  Global env ids rank*n_local ... feed terrain types and Philox counters (§8e)."""
     import numpy as np
     import torch
-    from shifu_b200 import hotpath
+    from shifu_b200.sim import fake_isaacgym
+    fake_isaacgym.install(device)
+    fake_isaacgym.reset_gym()
+    fake_isaacgym.set_default_device(device)
     from shifu_b200.sim.synthetic import a1_snapshot
-    ter, cfg = terrain or _terrain()
-    n_global = n_local * world
-    gid = torch.arange(rank * n_local, (rank + 1) * n_local)
-    # isaac_gym.py:342-344 on the GLOBAL env index, so results do not depend on the GPU count (§8e)
-    types = torch.div(gid, (n_global / cfg.terrain.num_cols), rounding_mode='floor').to(torch.long)
-    types.clamp_(max=cfg.terrain.num_cols - 1)
-    g = torch.Generator().manual_seed(seed + rank)
-    levels0 = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (n_local,), generator=g)
-    origins = torch.from_numpy(ter.env_origins).float()
-    env_origins = origins[levels0, types].to(device).contiguous()
+    from shifu_b200.tasks.a1_walking import A1Conditional, A1EnvConfig
+    cfg = A1EnvConfig()
+    cfg.num_envs, cfg.device = n_local, device
+    np.random.seed(0)                       # terrain generator (host numpy, one-time init)
+    torch.manual_seed(seed + rank)          # initial terrain levels
+    env = A1Conditional(cfg, fused=True, carry_body_frame=True, rng_seed=seed, env_offset=rank * n_local,
+                        num_envs_global=n_local * world, store_measured_heights=store_heights,
+                        use_cuda_graph=use_graph)
+    isg, hp = env.isg_env, env.hot
     snap = a1_snapshot(seed + rank, 1, n_local, gen_device=device, p_base=0.01, p_leg=0.1, xy_range=3.0,
                        offmap=False)
     root = snap.root_offset.clone()
-    root[:, :3] += env_origins
-    dof = snap.dof[4].reshape(n_local * 12, 2).contiguous()
-    contact = snap.contact.reshape(n_local * 17, 3).contiguous()
-    desc = hotpath.a1_desc(n_local, env_offset=rank * n_local, rng_seed=seed)
-    hp = hotpath.A1HotPath(desc, root_state=root.contiguous(), dof_state=dof, contact_state=contact,
-                           height_samples=torch.from_numpy(ter.heightsamples), terrain_origins=origins,
-                           terrain_types=types, env_origins=env_origins, carry_body_frame=carry,
-                           want_measured_heights=want_heights)
-    hp.ep_len.copy_(torch.randint(0, 500, (n_local,), generator=g).to(device))
-    hp.command.copy_((torch.rand(n_local, 3, generator=g) * 2 - 1).to(device))
-    hp.terrain_levels.copy_(levels0.to(device))
+    root[:, :3] += isg.env_origins
+    isg.root_state.copy_(root)
+    isg.dof_state.copy_(snap.dof[4].reshape(n_local * 12, 2))
+    isg.contact_state.copy_(snap.contact.reshape(n_local * 17, 3))
+    g = torch.Generator().manual_seed(seed + rank)
+    env.episode_length_buf = torch.randint(0, 500, (n_local,), generator=g).to(device)
+    env.command_buf.copy_((torch.rand(n_local, 3, generator=g) * 2 - 1).to(device))
+    env.terrain_levels.copy_(isg.terrain_levels)
     hp.sync_level_sum()
     hp.body_frame()             # seed the carried body-frame velocities from the initial root rows
-    raw_actions = snap.actions.contiguous()
-    return hp, raw_actions
+    raw = hp.action_input()     # the policy-output buffer of the captured step (no per-step action copy)
+    raw.copy_(snap.actions)
+    return env, raw
 
 
-LAUNCHES_PER_STEP = 4 + 1 + 1 + 1 + 1      # pd x4, fused post-physics, compaction, collect, publish
+def build_a1(n_local, rank, world, device, terrain=None, seed=1234, carry=True, want_heights=False):
+    """(hot path, raw actions) of build_env — for the dev tools that drive the kernels directly."""
+    env, raw = build_env(n_local, rank, world, device, seed=seed, store_heights=want_heights)
+    env.hot._env = env           # keep the env (and its simulator tensors) alive with the hot path
+    return env.hot, raw
 
 
-def time_resident(hp, raw_actions, steps, warmup, allreduce=None, barrier=None, flush=None):
-    """K steps on resident state.  Returns (total_ms, per-launch ms of the fused kernel)."""
+LAUNCHES_PER_STEP = 4 + 1 + 1 + 1 + 1      # pd x4, fused post-physics, compaction, collect, publish (libshifu_b200.so kernels;
+                                           # the action copy into the graph input buffer is torch's)
+
+
+def time_steps(env, raw_actions, steps, warmup, barrier=None, flush=None):
+    """K control steps through ``A1Conditional.step`` (the user-facing call) on resident state.
+    Returns the total device time in ms (CUDA events on the launching stream)."""
     import torch
     for _ in range(warmup):
-        hp.step_resident(raw_actions, allreduce=allreduce)
+        env.step(raw_actions)
     torch.cuda.synchronize()
     if barrier is not None:
         barrier()
     torch.cuda.synchronize()
-    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    total = 0.0
     if flush is None:
         t0.record()
-    for i in range(steps):
-        if flush is not None:
-            flush.zero_()
-            t0 = torch.cuda.Event(enable_timing=True)
-            t1 = torch.cuda.Event(enable_timing=True)
-            t0.record()
-        hp.pd_torque(raw_actions)
-        hp.pd_torque(); hp.pd_torque(); hp.pd_torque()
-        k0[i].record()
-        hp.post_physics()
-        k1[i].record()
-        hp.finalize(allreduce)
-        if flush is not None:
-            t1.record()
-            t1.synchronize()
-            total += t0.elapsed_time(t1)
-    if flush is None:
+        for _ in range(steps):
+            env.step(raw_actions)
         t1.record()
-    torch.cuda.synchronize()
-    if barrier is not None:
-        barrier()
-    if flush is None:
-        total = t0.elapsed_time(t1)
-    kern = [a.elapsed_time(b) for a, b in zip(k0, k1)]
-    return total, kern
+        env.hot.wait_stats()                 # side-stream all-reduce of the last step (N>1)
+        torch.cuda.synchronize()
+        if barrier is not None:
+            barrier()
+        return t0.elapsed_time(t1)
+    total = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        env.step(raw_actions)
+        t1.record()
+        t1.synchronize()
+        total += t0.elapsed_time(t1)
+    return total
+
+
+def time_fused_kernel(hp, launches=20):
+    """CUDA-event duration of the fused post-physics launch alone (the roofline's kernel), on the
+    stream it is launched on; state + obs are larger than L2, so every launch streams from HBM."""
+    import torch
+    ms = []
+    for i in range(launches + 3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        hp.post_physics()
+        b.record()
+        b.synchronize()
+        hp.finalize()
+        if i >= 3:
+            ms.append(a.elapsed_time(b))
+    return ms
+
+
+def measure_traffic_live(n):
+    """dram__bytes_read + dram__bytes_write of one fused launch, from a one-kernel ncu capture of a
+    child process (only when ncu is on PATH and profiling is permitted); None otherwise."""
+    import shutil
+    ncu = shutil.which("ncu")
+    if ncu is None or os.environ.get("SHIFU_BENCH_NO_NCU"):
+        return None, "ncu not on PATH"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:a1_post_physics_tma", "-s", "4", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "ncu_run.py")]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, N=str(n)))
+    except (subprocess.TimeoutExpired, OSError) as exc:
+        return None, f"ncu failed: {exc}"
+    total = 0.0
+    for line in r.stdout.splitlines():
+        cells = [c.strip('"') for c in line.split('","')]
+        if len(cells) > 3 and cells[-3].startswith("dram__bytes_"):
+            unit, val = cells[-2], float(cells[-1].replace(",", ""))
+            total += val * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    if total <= 0:
+        return None, "ncu produced no dram metrics (profiling not permitted?)"
+    return total, "measured live (ncu, one launch)"
 
 
 def time_graph(hp, raw_actions, steps, warmup):
-    """Same step captured once into a CUDA graph (device-resident step counter) — the launch-bound
-    small-N configurations."""
+    """The step as CUDA-graph replays through the hot path's own graph_step (what the class API uses
+    on resident state)."""
     import torch
-    hp.step_dev.fill_(hp.step_counter + 1)
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        for _ in range(2):
-            hp.step_resident(raw_actions, use_step_dev=True)
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        hp.step_resident(raw_actions, use_step_dev=True)
-    for _ in range(warmup):
-        g.replay()
+    for _ in range(warmup + 3):
+        hp.graph_step(raw_actions)
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(steps):
-        g.replay()
+        hp.graph_step(raw_actions)
     t1.record()
     torch.cuda.synchronize()
     return t0.elapsed_time(t1)
@@ -289,10 +321,11 @@ def time_camera(n, device, flush, peak, steps=20, warmup=5, h=128, w=128):
                     "(sensors.py:165-188); 32 B/pixel"}
 
 
-def time_e2e(hp, raw_actions, steps, warmup):
-    """Same step through the public host API with HOST buffers: every step copies the simulator
-    state + actions from pinned host memory and reads obs / reward / reset flags back."""
+def time_e2e(env, raw_actions, steps, warmup):
+    """Same step through the public class API (``A1Conditional.step``) with HOST buffers: every step
+    copies the simulator state + actions from pinned host memory and reads obs / reward / reset flags back."""
     import torch
+    hp = env.hot
     n = hp.n
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t.cpu())
     h_root, h_dof, h_contact, h_act = pin(hp.root_state), pin(hp.dof_state), pin(hp.contact_state), pin(raw_actions)
@@ -326,7 +359,7 @@ def time_e2e(hp, raw_actions, steps, warmup):
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in)
             s_cmp.wait_event(ev_out)
-            hp.step_resident(d_act)
+            env.step(d_act)
             ev_cmp.record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp)
@@ -351,54 +384,78 @@ def time_e2e(hp, raw_actions, steps, warmup):
 # CPU arm: the oracle port of the reference's torch-CPU path
 # ---------------------------------------------------------------------------------------------
 
-def cpu_oracle_rate(n, steps, warmup=1, seed=1234):
+def cpu_oracle_rate(n, steps, warmup=1, seed=1234, shard=131072):
     """env-steps/s of oracle/shifu_oracle.py (torch CPU, all host threads) on the same synthetic
-    workload, n envs.  bench.py's only use of oracle/: as the reported CPU baseline."""
-    import numpy as np
+    workload, n envs per step, processed in contiguous shards of at most `shard` envs (bounded host
+    memory; the envs are independent).  bench.py's only use of oracle/: the reported CPU baseline and
+    the --impl reference arm."""
     import torch
     from oracle import shifu_oracle as so
     from shifu_b200.sim.synthetic import a1_snapshot
     torch.set_num_threads(os.cpu_count() or 1)
     ter, cfg = _terrain()
-    types = torch.div(torch.arange(n), (n / cfg.terrain.num_cols), rounding_mode='floor').to(torch.long)
-    g = torch.Generator().manual_seed(seed)
-    levels0 = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (n,), generator=g)
     origins = torch.from_numpy(ter.env_origins).float()
-    p = so.A1Params(n=n, rng_seed=seed)
-    st = so.a1_new_state(p, torch.from_numpy(ter.heightsamples), origins, types, origins[levels0, types])
-    st.ep_len[:] = torch.randint(0, 500, (n,), generator=g)
-    st.command[:] = torch.rand(n, 3, generator=g) * 2 - 1
-    hpts = p.height_points()
-    snap = a1_snapshot(seed, 1, n, p_base=0.01, p_leg=0.1, xy_range=3.0, offmap=False)
+    hs = torch.from_numpy(ter.heightsamples)
+    parts = []
+    for off in range(0, n, shard):
+        m = min(shard, n - off)
+        gid = torch.arange(off, off + m)
+        types = torch.div(gid, (n / cfg.terrain.num_cols), rounding_mode='floor').to(torch.long).clamp_(max=cfg.terrain.num_cols - 1)
+        g = torch.Generator().manual_seed(seed + off)
+        levels0 = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (m,), generator=g)
+        p = so.A1Params(n=m, rng_seed=seed, env_offset=off)
+        st = so.a1_new_state(p, hs, origins, types, origins[levels0, types])
+        st.ep_len[:] = torch.randint(0, 500, (m,), generator=g)
+        st.command[:] = torch.rand(m, 3, generator=g) * 2 - 1
+        parts.append((p, st, p.height_points(), a1_snapshot(seed + off, 1, m, p_base=0.01, p_leg=0.1, xy_range=3.0,
+                                                            offmap=False)))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        so.a1_step(p, st, snap.actions, snap, hpts)
+        for p, st, hpts, snap in parts:
+            so.a1_step(p, st, snap.actions, snap, hpts)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return n / statistics.median(times), statistics.median(times) * 1e3
+    return n / statistics.median(times), statistics.median(times) * 1e3, sum(times)
 
 
 def run_reference(args):
+    """The reference's torch-CPU path (oracle port; the reference itself is Python and does not travel to
+    the GPU box) on the SAME workload as our arm: args.envs_per_gpu envs per step, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 65536
-    rate, ms = cpu_oracle_rate(n, steps=max(args.steps, 1), warmup=min(args.warmup, 2))
+    n = args.envs_per_gpu
+    steps, warmup = max(args.steps, 1), min(args.warmup, 2)
+    budget = float(os.environ.get("SHIFU_REF_BUDGET_S", "150"))
+    probe_rate, probe_ms, _ = cpu_oracle_rate(65536, steps=2, warmup=1)
+    est = (steps + warmup) * n / probe_rate
+    sample = n
+    while est > budget and sample > 65536:            # bounded run: shrink the sample, say so
+        sample //= 2
+        est = (steps + warmup) * sample / probe_rate
+    rate, ms, spent = cpu_oracle_rate(sample, steps=steps, warmup=warmup)
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "a1_conditional post-physics step incl. 187-pt heightfield scan + PD torques, "
-                               f"{ENVS_PER_GPU} envs/GPU", "sample_envs": n},
+        "config": _config(n, 1),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle/shifu_oracle.py a1_step (torch CPU restatement of the reference, "
-                                   f"bit-identical to it), {n} envs x {args.steps} steps, median"},
+                         "sample_envs": sample, "same_env_count_as_gpu_arm": sample == n,
+                         "rate_65536_envs": probe_rate,
+                         "sample": f"oracle/shifu_oracle.py a1_step (torch CPU restatement, bit-identical to the "
+                                   f"reference), {sample} envs/step in shards of 131072, {steps} steps, median"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+def _config(n, world):
+    return {"workload": "a1_conditional post-physics step incl. 187-pt heightfield scan + PD torques, "
+                        f"{n} envs/GPU (BASELINE configs[2]; configs[4] when n_gpus=8)",
+            "envs_per_gpu": n, "decimation": 4}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -414,21 +471,25 @@ def run_ours(args):
                          "use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
-    allreduce = barrier = None
+    barrier = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(device))
-        allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
         barrier = dist.barrier
     n = args.envs_per_gpu
-    terrain = _terrain()
-    hp, raw = build_a1(n, rank, world, device, terrain)
+    # the headline instantiation: class API, carried body-frame velocities, measured_heights not kept
+    # (B_alg of SURVEY.md 8d excludes that optional tensor); the store-everything instantiation is
+    # measured right after and reported beside it
+    env, raw = build_env(n, rank, world, device, store_heights=False)
+    if world > 1:
+        env.stats_allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    hp = env.hot
     peak, peak_src = _peaks()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms, kern_ms = time_resident(hp, raw, args.steps, args.warmup, allreduce, barrier)
+    total_ms = time_steps(env, raw, args.steps, args.warmup, barrier)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms], device=device, dtype=torch.double)
     if world > 1:
@@ -436,74 +497,100 @@ def run_ours(args):
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3)
+    kern_ms = time_fused_kernel(hp)
     kms = statistics.mean(kern_ms)
     achieved = B_ALG_POST * n / (kms * 1e-3) / 1e9
     reset_frac = float(hp.n_reset.item()) / n
+    graphed = hp._graph is not None
 
     line = None
     if rank == 0:
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get("a1_post_physics_kernel_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "a1_conditional post-physics step incl. 187-pt heightfield scan + PD torques, "
-                                   f"{n} envs/GPU (BASELINE configs[2]; configs[4] when n_gpus=8)",
-                       "envs_per_gpu": n, "global_envs": n * world, "decimation": 4,
-                       "l2": "inputs larger than L2 (state + obs = %.0f MB per GPU vs 126 MB L2); no flush"
-                             % ((B_ALG_POST + 4 * B_ALG_PD) * n / 1e6),
-                       "reset_fraction_per_step": reset_frac, "launch": "direct (8 launches/step)",
-                       "collective": "all_reduce(16 x f64) per step" if world > 1 else "none"},
-            "roofline": {"bound": "hbm", "kernel": "a1_post_physics_tma_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "config": dict(_config(n, world), global_envs=n * world,
+                           api="shifu_b200.tasks.a1_walking.A1Conditional.step on the stand-in simulator (resident state)",
+                           instantiation="carry_body_frame=True, measured_heights not stored (HAS_MROW=0)",
+                           l2="inputs larger than L2 (state + obs = %.0f MB per GPU vs 126 MB L2); no flush"
+                              % ((B_ALG_POST + 4 * B_ALG_PD) * n / 1e6),
+                           reset_fraction_per_step=reset_frac,
+                           launch="one CUDA-graph replay per step (9 kernels)" if graphed else "direct (9 launches/step)",
+                           collective="all_reduce(16 x f64) per step on a side stream" if world > 1 else "none"),
+            "roofline": {"bound": "hbm", "kernel": "a1_post_physics_tma_kernel<0,0>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_env": B_ALG_POST,
                          "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step,
                          "step_frac": (B_ALG_POST + 4 * B_ALG_PD) * n / (ms_per_step * 1e-3) / 1e9 / peak},
             "clocks": clocks, "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         }
-    # ---- N=1 extras: e2e through host buffers, the size sweep, the CPU baseline -----------------
+    # ---- N=1 extras: e2e through host buffers, the other instantiation, the size sweep, the CPU baseline
     if world == 1 and args.quick:
         pass
     elif world == 1:
-        e_ms, h2d, d2h, _ = time_e2e(hp, raw, min(40, max(3, args.steps // 4)), 2)
         e_steps = min(40, max(3, args.steps // 4))
+        e_ms, h2d, d2h, _ = time_e2e(env, raw, e_steps, 2)
         line["e2e"] = {"value": n / (e_ms / e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / e_steps,
-                       "note": "pinned host state+actions -> device, step, obs+rew+reset -> pinned host; upload of step t+1 overlaps read-back of step t (3 streams); PCIe-bound"}
-        del hp
+                       "note": "A1Conditional.step with pinned host state+actions -> device, obs+rew+reset -> pinned host; "
+                               "upload of step t+1 overlaps read-back of step t (3 streams); PCIe-bound"}
+        # a longer timed region than the driver's K, for the record
+        long_ms = time_steps(env, raw, 200, 5)
+        line["value_200_steps"] = n / (long_ms / 200 * 1e-3)
+        if os.environ.get("SHIFU_BENCH_TRAFFIC", "1") != "0":
+            tr, how = measure_traffic_live(n)
+            if tr is None:
+                tpath = os.path.join(ROOT, "profiles", "traffic.json")
+                if os.path.exists(tpath):
+                    with open(tpath) as f:
+                        tr = json.load(f).get("a1_post_physics_kernel_bytes_per_launch")
+                    how = f"from profiles/traffic.json ({how})"
+            line["roofline"]["traffic"], line["roofline"]["traffic_source"] = tr, how
+        del env, hp
+        torch.cuda.empty_cache()
+        # the store-everything instantiation of the class API (measured_heights kept: +748 B/env written)
+        env2, raw2 = build_env(n, 0, 1, device, store_heights=True)
+        tot2 = time_steps(env2, raw2, args.steps, args.warmup)
+        k2 = statistics.mean(time_fused_kernel(env2.hot))
+        line["with_measured_heights"] = {
+            "value": n / (tot2 / args.steps * 1e-3), "ms_per_step": tot2 / args.steps, "kernel": "a1_post_physics_tma_kernel<0,1>",
+            "kernel_ms": k2, "algorithmic_bytes_per_env": B_ALG_POST + 748,
+            "frac": (B_ALG_POST + 748) * n / (k2 * 1e-3) / 1e9 / peak,
+            "frac_on_1819_bytes": B_ALG_POST * n / (k2 * 1e-3) / 1e9 / peak}
+        del env2
         torch.cuda.empty_cache()
         sweep = []
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
         for m in SWEEP:
-            h2, r2 = build_a1(m, 0, 1, device, terrain)
-            tot, km = time_resident(h2, r2, 20, 5, flush=flush)
-            gms = time_graph(h2, r2, 200, 20) / 200
+            e_direct, r2 = build_env(m, 0, 1, device, use_graph=False)
+            tot = time_steps(e_direct, r2, 20, 5, flush=flush)
+            km = statistics.mean(time_fused_kernel(e_direct.hot, 10))
+            del e_direct
+            e_graph, r3 = build_env(m, 0, 1, device, use_graph=True)
+            gms = time_steps(e_graph, r3, 200, 20) / 200
             sweep.append({"envs": m, "ms_per_step_l2_flushed": tot / 20, "env_steps_per_s_l2_flushed": m / (tot / 20 * 1e-3),
                           "ms_per_step_graph_l2_warm": gms, "env_steps_per_s_graph_l2_warm": m / (gms * 1e-3),
-                          "fused_kernel_ms": statistics.mean(km)})
-            del h2
+                          "fused_kernel_ms": km, "api": "A1Conditional.step"})
+            del e_graph
         line["sweep"] = sweep
         line["abb_prior_stage"] = time_abb(65536, device, flush)
         line["camera_gather"] = time_camera(2048, device, flush, peak)
         if not args.no_cpu:
-            rate, ms = cpu_oracle_rate(65536, steps=5, warmup=1)
-            rate4k, ms4k = cpu_oracle_rate(4096, steps=20, warmup=3)
+            rate, ms, _ = cpu_oracle_rate(262144, steps=8, warmup=1)
+            rate4k, ms4k, _ = cpu_oracle_rate(4096, steps=20, warmup=3)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "oracle a1_step (torch CPU, all cores), 65536 envs x 5 steps, median "
-                                              f"{ms:.0f} ms/step; 4096 envs (BASELINE configs[0]): {rate4k:.3g} env-steps/s"}
+                                    "sample_envs": 262144, "rate_4096_envs": rate4k,
+                                    "sample": "oracle a1_step (torch CPU, all cores), 262144 envs x 8 steps "
+                                              f"(2 shards), median {ms:.0f} ms/step"}
     else:
-        line_e2e = None
         e_steps = min(40, max(3, args.steps // 4))
-        e_ms, h2d, d2h, _ = time_e2e(hp, raw, e_steps, 2)
+        e_ms, h2d, d2h, _ = time_e2e(env, raw, e_steps, 2)
         t = torch.tensor([e_ms], device=device, dtype=torch.double)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             line["e2e"] = {"value": n * world / (float(t.item()) / e_steps * 1e-3), "unit": UNIT,
-                           "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world}
+                           "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                           "ms_per_step": float(t.item()) / e_steps}
     if rank == 0:
         _emit(line)
     if world > 1:

@@ -217,11 +217,26 @@ def bind_a1(env, hp):
     env.extras.update(hp.extras())
 
 
+def _resident_state(env) -> bool:
+    """True when nothing runs between the kernel launches of a step: the stand-in simulator with no
+    snapshot provider (state resident in HBM, refresh calls are no-ops) and no cross-rank collective."""
+    sim = env.isg_env.sim
+    return (getattr(sim, "provider", 0) is None and env.stats_allreduce is None
+            and not getattr(env.isg_env.gym, "needs_indexed_resets", True) and getattr(env, "use_cuda_graph", True))
+
+
 def a1_fused_step(env, hp, actions: torch.Tensor):
     """ShifuVecEnv.step (env.py:85-106) with the A1 hooks, as kernel launches around the simulator
-    crossings of A1Robot.step / IsaacGymEnv.refresh_state (a1_conditional.py:64-75, isaac_gym.py:139-154)."""
+    crossings of A1Robot.step / IsaacGymEnv.refresh_state (a1_conditional.py:64-75, isaac_gym.py:139-154).
+    On resident state (no simulator between the launches) the whole step is one CUDA-graph replay."""
     gym, sim, rb, isg = env.isg_env.gym, env.isg_env.sim, env.robot, env.isg_env
     actions = actions.contiguous()
+    env.common_step_counter += 1
+    hp.step_counter = env.common_step_counter - 1
+    if _resident_state(env):
+        hp.graph_step(actions, isg.decimation)
+        env.extras.update(hp.extras())
+        return env.obs_buf, env.privileged_obs_buf, env.rew_buf, env.reset_buf, env.extras
     for i in range(isg.decimation):
         hp.pd_torque(actions if i == 0 else None)
         rb._internal_motor_step(rb.torques)
@@ -231,8 +246,6 @@ def a1_fused_step(env, hp, actions: torch.Tensor):
         hp.body_frame()                                                 # S_prev root
     rb.apply_force_on_base(rb.rand_force_buf.view(-1, 3))
     isg.refresh_state()
-    env.common_step_counter += 1
-    hp.step_counter = env.common_step_counter - 1
     hp.post_physics()
     hp.finalize(env.stats_allreduce)
     if getattr(gym, "needs_indexed_resets", True):

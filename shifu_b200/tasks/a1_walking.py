@@ -129,12 +129,15 @@ class A1Conditional(ShifuVecEnv):
     TERMS = ("tracking_lin_vel", "tracking_ang_vel", "stabilizing_base", "smoothing_action", "leg_collision",
              "torques_penalize")
 
-    def __init__(self, cfg, fused: bool = True, carry_body_frame: bool = False, rng_seed: int = 0x5EED,
-                 env_offset: int = 0, num_envs_global: int = None):
+    def __init__(self, cfg, fused: bool = True, carry_body_frame: bool = True, rng_seed: int = 0x5EED,
+                 env_offset: int = 0, num_envs_global: int = None, store_measured_heights: bool = True,
+                 use_cuda_graph: bool = True):
         super().__init__(cfg, env_offset=env_offset, num_envs_global=num_envs_global)
         self.auto_fuse = False          # this class wires its own fusion (explicit fused= switch)
         self.fused = fused
         self.rng_seed = rng_seed
+        self.use_cuda_graph = use_cuda_graph
+        self._store_heights = store_measured_heights
         self.robot = A1Robot(A1ActorConfig())
         self.robot.task = self
         self.isg_env.create_envs(robot=self.robot)
@@ -176,7 +179,8 @@ class A1Conditional(ShifuVecEnv):
         hp = hotpath.A1HotPath(desc, root_state=isg.root_state, dof_state=isg.dof_state,
                                contact_state=isg.contact_state, height_samples=isg.height_samples,
                                terrain_origins=isg.terrain_origins, terrain_types=isg.terrain_types,
-                               env_origins=isg.env_origins, terms=names, carry_body_frame=carry_body_frame)
+                               env_origins=isg.env_origins, terms=names, carry_body_frame=carry_body_frame,
+                               want_measured_heights=self._store_heights)
         self.hot = hp
         # the env / robot attributes ARE the tensors the kernel reads and writes
         self.actions, self.obs_buf, self.rew_buf, self.reset_buf = hp.actions, hp.obs_buf, hp.rew_buf, hp.reset_buf
@@ -206,24 +210,8 @@ class A1Conditional(ShifuVecEnv):
     def step(self, actions: torch.Tensor):
         if not self.fused:
             return super().step(actions * 0.5)                              # a1_conditional.py:122-124
-        hp, gym, sim, rb = self.hot, self.isg_env.gym, self.isg_env.sim, self.robot
-        actions = actions.contiguous()
-        for i in range(self.isg_env.decimation):                            # a1_conditional.py:64-72
-            hp.pd_torque(actions if i == 0 else None)
-            rb._internal_motor_step(rb.torques)
-            gym.simulate(sim)
-            gym.refresh_dof_state_tensor(sim)
-        if not hp.carry_body_frame:
-            hp.body_frame()                                                 # :73 (S_prev root, D7)
-        rb.apply_force_on_base(rb.rand_force_buf.view(-1, 3))               # :75
-        self.isg_env.refresh_state()
-        self.common_step_counter += 1
-        hp.step_counter = self.common_step_counter - 1
-        hp.post_physics()
-        hp.finalize(self.stats_allreduce)
-        self._push_resets_to_sim()
-        self.extras.update(hp.extras())            # this step's own slot of the extras ring (fresh inner dict)
-        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+        from shifu_b200.gym import autofuse
+        return autofuse.a1_fused_step(self, self.hot, actions)       # kernel launches, or one graph replay
 
     def reset(self):
         if not self.fused:
