@@ -352,6 +352,38 @@ int shifu_history_add(ShifuCtx* ctx, float* history, const float* x, int32_t n, 
 /* torch.clip(x, -c, c) (env.py:87,90), in place or out of place. */
 int shifu_clip(ShifuCtx* ctx, const float* in, float* out, int64_t count, float c, void* stream);
 
+/* ---- row N3: Terrain height map on the device ---------------------------------
+ * Replaces the tile-by-tile numpy assembly of shifu/utils/terrain.py:42-173 (make_terrain 106-152,
+ * add_terrain_to_map 154-173, gap_terrain / pit_terrain 176-198).  The caller lists one record per
+ * tile; generators that draw random numbers (coarse noise grid, obstacle rectangles, stone heights)
+ * find them in `table` (float64), written by the host in the generator's own draw order. */
+enum ShifuTerrainKind {
+  SHIFU_TERRAIN_PYRAMID = 0,        /* p = {peak, platform half-width px}                 pyramid_sloped_terrain */
+  SHIFU_TERRAIN_PYRAMID_NOISE = 1,  /* p = {peak, half, nx, ny}; table: nx*ny coarse heights   + random_uniform_terrain */
+  SHIFU_TERRAIN_STAIRS = 2,         /* p = {step width px, step height units, platform px}     pyramid_stairs_terrain */
+  SHIFU_TERRAIN_OBSTACLES = 3,      /* p = {num rects, platform px}; table: (sx, sy, w, l, h) per rect */
+  SHIFU_TERRAIN_STONES = 4,         /* p = {stone px, distance px, platform px, depth units}; table: height per stone */
+  SHIFU_TERRAIN_GAP = 5,            /* p = {gap px, platform px}                          terrain.py:176-187 */
+  SHIFU_TERRAIN_PIT = 6             /* p = {depth units, platform half px}                terrain.py:190-198 */
+};
+typedef struct ShifuTerrainTile {
+  int32_t kind;        /* enum ShifuTerrainKind */
+  int32_t i, j;        /* curriculum level (row of tiles) and terrain type (column of tiles) */
+  int32_t p[4];
+  int32_t table_off;   /* first entry of this tile in `table` */
+} ShifuTerrainTile;
+typedef struct ShifuTerrainDesc {
+  int32_t num_rows, num_cols;          /* tiles */
+  int32_t width_px, length_px;         /* tile size in cells (terrain.py:59-60) */
+  int32_t border_px;                   /* terrain.py:62 */
+  double env_length, env_width;        /* metres */
+  double horizontal_scale, vertical_scale;
+} ShifuTerrainDesc;
+/* tiles / table: HOST arrays (n_tiles records, n_table doubles); height_map: device int16
+ * (tot_rows x tot_cols, zero-filled border included); origins: device float64 (num_rows, num_cols, 3). */
+int shifu_terrain_generate(ShifuCtx* ctx, const ShifuTerrainDesc* desc, const ShifuTerrainTile* tiles, int32_t n_tiles,
+                           const double* table, int32_t n_table, int16_t* height_map, double* origins, void* stream);
+
 /* ---- step statistics (row a11 logging, §8e collective payload) ------------------------------
  * After *_post_physics: move the step's stats (double[SHIFU_NUM_STATS]) into stats_out and clear
  * the accumulator; when step_dev_to_advance != NULL that device counter is incremented (the

@@ -114,6 +114,18 @@ class CameraGatherIO(C.Structure):
     ]
 
 
+class TerrainTile(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("i", C.c_int32), ("j", C.c_int32), ("p", C.c_int32 * 4), ("table_off", C.c_int32)]
+
+
+class TerrainDesc(C.Structure):
+    _fields_ = [("num_rows", C.c_int32), ("num_cols", C.c_int32), ("width_px", C.c_int32), ("length_px", C.c_int32),
+                ("border_px", C.c_int32), ("env_length", C.c_double), ("env_width", C.c_double),
+                ("horizontal_scale", C.c_double), ("vertical_scale", C.c_double)]
+
+
+TERRAIN_PYRAMID, TERRAIN_PYRAMID_NOISE, TERRAIN_STAIRS, TERRAIN_OBSTACLES, TERRAIN_STONES, TERRAIN_GAP, TERRAIN_PIT = range(7)
+
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -142,6 +154,8 @@ SIGNATURES = {
     "shifu_publish_extras": [_VP, _VP, _VP, _VP],
     "shifu_publish_extras_ring": [_VP, _VP, _VP, _I32, _I32, _VP, _VP],
     "shifu_read_stats_host": [_VP, _VP, _VP],
+    "shifu_terrain_generate": [_VP, C.POINTER(TerrainDesc), C.POINTER(TerrainTile), _I32, C.POINTER(C.c_double), _I32,
+                               _VP, _VP, _VP],
 }
 _RESTYPES = {"shifu_last_error": C.c_char_p}
 

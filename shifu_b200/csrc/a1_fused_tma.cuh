@@ -73,6 +73,10 @@ constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;
 constexpr int V3_SCAN_BASE = V3_B_THREADS;
 constexpr int V3_DMA_BASE = V3_B_THREADS + V3_C_THREADS;
 static_assert(V3_SCAN_WARPS == 6 || V3_SCAN_WARPS == 12, "scan group: 6 or 12 warps");
+#if defined(V3_OBS_TMA) && V3_SCAN_WARPS != 12
+#error "V3_OBS_TMA is written for the 12-warp scan group (two half-groups of 6 warps)"
+#endif
+constexpr uint32_t V3_OBS_CHUNK_BYTES = 8 * A1_OBS * 4;      // 8288 = 16 * 518
 
 struct alignas(128) V3In {            // one tile of simulator/env rows, each member 16-B aligned
   float root[A1_TILE][13];            //  1664 B
@@ -106,6 +110,12 @@ struct alignas(128) V3Smem {
   // accumulates this tile's
   float rterm[2][SHIFU_MAX_REWARD_TERMS][A1_TILE];
   uint64_t full_in[V3_STAGES], e_done[V3_STAGES], b_done[V3_STAGES], h_done[V3_STAGES];
+#ifdef V3_OBS_TMA
+  // obs rows of the tile, staged as in global memory (row pitch 259 floats): [half-group][item][8 envs]
+  // — a chunk of 8 consecutive envs is one contiguous, 16-byte aligned 8288-byte span on both sides,
+  // written back with ONE bulk copy instead of 8 x 259 scattered 4-byte stores
+  alignas(16) float obs[2][2][8 * A1_OBS];
+#endif
 #ifdef V3_PROFILE
   long long t_issue[V3_STAGES];
 #endif
@@ -440,6 +450,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
   {
     const int p = t - V3_SCAN_BASE;                          // index in the scan group
     const int sw = p >> 5, lane = p & 31;
+#ifdef V3_OBS_TMA
+    constexpr int V3_HALF_THREADS = V3_C_THREADS / 2;         // a half-group = 6 warps = the 16 envs of two items
+    const int hg = p / V3_HALF_THREADS, hl = p % V3_HALF_THREADS;
+#endif
     const float hclip = fminf(k.h_clip, k.clip_obs);         // clip(clip(v,+-a),+-b) == clip(v,+-min(a,b))
     const unsigned max_px = (unsigned)(k.trows - 1), max_py = (unsigned)(k.tcols - 1);
     // banded index: (px>>3)*8*W + py*8 + (px&7)  ==  (px & ~7)*(W-1) + px + 8*py    (3 integer ops)
@@ -483,7 +497,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       V3_TICK(16);
       {
         // item -> (scan point of this lane, first env pair of the batch)
-        struct Item { float bx, by; int q0, pt; bool live; };
+        struct Item { float bx, by; int q0, pt, it; bool live; };
         auto item = [&](int it) {
           int g, qb;
           if (V3_SCAN_WARPS == 12) { g = sw % 6; qb = 2 * (sw / 6) + it; }
@@ -494,6 +508,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           r.pt = r.live ? raw : A1_POINTS - 1;                // idle lanes shadow the last point, stores masked
           r.bx = k.px[r.pt % A1_NX]; r.by = k.py[r.pt / A1_NX];
           r.q0 = 4 * qb;
+          r.it = it;
           return r;
         };
         // Index arithmetic of one item in packed fp32x2 (two envs per instruction).
@@ -553,24 +568,43 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           for (int u = 0; u < 8; ++u) h[u] = v3_gather(table + idx[u]);      // isaac_gym.py:427-431 (folded)
         };
         auto store_batch = [&](const Item& w, const int (&h)[8]) {
+#ifdef V3_OBS_TMA
+          float* ob = &s.obs[hg][w.it][A1_HEAD + w.pt];                       // row u of the chunk: + u * A1_OBS
+#else
           float* ob = io.obs_buf + (e0 + 2 * w.q0) * A1_OBS + A1_HEAD + w.pt;
+#endif
           float* mb = HAS_MROW ? io.measured_heights + (e0 + 2 * w.q0) * A1_POINTS + w.pt : nullptr;
-          if (!w.live) return;
+          if (w.live) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u].z);
-            const f2_t hg = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
-            float v0, v1;
-            upk(SUB2(pk(zb.x, zb.y), hg), v0, v1);                            // (z - 0.5) - h, a1_conditional.py:132
-            v3_store(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
-            v3_store(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
-            if (HAS_MROW) {
-              float g0, g1;
-              upk(hg, g0, g1);
-              __stcs(mb + (2 * u) * A1_POINTS, g0);
-              __stcs(mb + (2 * u + 1) * A1_POINTS, g1);
+            for (int u = 0; u < 4; ++u) {
+              const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u].z);
+              const f2_t hg2 = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
+              float v0, v1;
+              upk(SUB2(pk(zb.x, zb.y), hg2), v0, v1);                           // (z - 0.5) - h, a1_conditional.py:132
+#ifdef V3_OBS_TMA
+              ob[(2 * u) * A1_OBS] = clampf(v0, -hclip, hclip);
+              ob[(2 * u + 1) * A1_OBS] = clampf(v1, -hclip, hclip);
+#else
+              v3_store(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
+              v3_store(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
+#endif
+              if (HAS_MROW) {
+                float g0, g1;
+                upk(hg2, g0, g1);
+                __stcs(mb + (2 * u) * A1_POINTS, g0);
+                __stcs(mb + (2 * u + 1) * A1_POINTS, g1);
+              }
             }
           }
+#ifdef V3_OBS_TMA
+          // chunk complete (head rows + every point group's columns): one bulk store of 8 rows
+          pipe::fence_proxy_async();
+          pipe::named_barrier(2 + hg, V3_HALF_THREADS);
+          if (hl == 0) {
+            pipe::bulk_store(io.obs_buf + (e0 + 2 * w.q0) * A1_OBS, &s.obs[hg][w.it][0], V3_OBS_CHUNK_BYTES);
+            pipe::bulk_commit();
+          }
+#endif
         };
         // Rolled software pipeline (the body stays small enough for the instruction cache shared with
         // the other warp roles): the gathers of item i are issued at the END of a trip and consumed
@@ -588,21 +622,33 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         V3_TICK(20);
         V3_WAIT(V3_POLL_SCAN, &s.b_done[b], par);
         V3_TICK(8);
+#ifdef V3_OBS_TMA
+        // the bulk stores of the previous tile must have finished READING the obs buffers before the
+        // head rows of this tile go in (the issuing thread waits, the half-group barrier publishes it)
+        if (hl == 0) pipe::bulk_wait_read_all();
+        pipe::named_barrier(2 + hg, V3_HALF_THREADS);
+#endif
         {
           V3In& in = s.in[b];
           const float c = k.clip_obs;
           for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
             const int e = i / A1_DOF, d = i - e * A1_DOF;
+#ifdef V3_OBS_TMA
+            float* hrow = &s.obs[e >> 4][(e >> 3) & 1][(e & 7) * A1_OBS];
+#define V3_HEAD_ST(ptr, v) (*(ptr) = (v))
+#else
             float* hrow = io.obs_buf + (e0 + e) * A1_OBS;
+#define V3_HEAD_ST(ptr, v) __stcs(ptr, v)
+#endif
             const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
             const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
                         a2 = in.hist[e][d * A1_HIST + 2];
 #ifndef V3_WI_NOHEAD
-            __stcs(hrow + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
-            __stcs(hrow + 24 + d, clampf(qd.y, -c, c));
-            __stcs(hrow + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
-            __stcs(hrow + 48 + d, clampf(a1, -c, c));
-            __stcs(hrow + 60 + d, clampf(a2, -c, c));
+            V3_HEAD_ST(hrow + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
+            V3_HEAD_ST(hrow + 24 + d, clampf(qd.y, -c, c));
+            V3_HEAD_ST(hrow + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
+            V3_HEAD_ST(hrow + 48 + d, clampf(a1, -c, c));
+            V3_HEAD_ST(hrow + 60 + d, clampf(a2, -c, c));
 #endif
             in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
             in.hist[e][d * A1_HIST + 1] = a0;
@@ -612,7 +658,11 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             const int e = i / 12, q = i - e * 12;
             const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
 #ifndef V3_WI_NOHEAD
+#ifdef V3_OBS_TMA
+            s.obs[e >> 4][(e >> 3) & 1][(e & 7) * A1_OBS + q] = clampf(v, -c, c);
+#else
             __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
+#endif
 #endif
           }
           // carried body-frame velocities for the next control step (robot.py:222-229, D7): one
@@ -653,6 +703,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       V3_TICK(17);
       V3_COUNT(18);
     }
+#ifdef V3_OBS_TMA
+    if (hl == 0) pipe::bulk_wait_all();                         // obs rows written before the CTA exits
+#endif
   }
 }
 

@@ -16,6 +16,7 @@
 #include "arm_ik.cuh"
 #include "camera_gather.cuh"
 #include "common_kernels.cuh"
+#include "terrain_gen.cuh"
 
 using namespace shifu;
 
@@ -623,6 +624,37 @@ extern "C" int shifu_publish_extras_ring(ShifuCtx* c, const double* stats, float
   publish_extras_kernel<<<1, 32, 0, S(stream)>>>(stats, ring, slots, slot, reinterpret_cast<const long long*>(step_dev),
                                                  ls, nt);
   CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_terrain_generate(ShifuCtx* c, const ShifuTerrainDesc* d, const ShifuTerrainTile* tiles, int32_t n_tiles,
+                                      const double* table, int32_t n_table, int16_t* map, double* origins, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(d); REQUIRE_PTR(tiles); REQUIRE_PTR(map); REQUIRE_PTR(origins);
+  if (n_tiles <= 0 || n_tiles > d->num_rows * d->num_cols) return fail(SHIFU_E_RANGE, "n_tiles=%d out of range", n_tiles);
+  if (n_table < 0 || (n_table > 0 && table == nullptr)) return fail(SHIFU_E_NULL, "table is NULL");
+  if (d->width_px <= 1 || d->length_px <= 1 || d->width_px != d->length_px)
+    return fail(SHIFU_E_RANGE, "tiles must be square (terrain.py:100-104 builds SubTerrain(width, width))");
+  const int tot_rows = d->num_rows * d->length_px + 2 * d->border_px, tot_cols = d->num_cols * d->width_px + 2 * d->border_px;
+  ShifuTerrainTile* d_tiles = nullptr; double* d_table = nullptr;
+  CUDA_TRY(cudaMalloc(&d_tiles, sizeof(ShifuTerrainTile) * n_tiles));
+  cudaError_t e = cudaMalloc(&d_table, sizeof(double) * (n_table > 0 ? n_table : 1));
+  if (e != cudaSuccess) { cudaFree(d_tiles); return fail((int)e, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  cudaMemcpyAsync(d_tiles, tiles, sizeof(ShifuTerrainTile) * n_tiles, cudaMemcpyHostToDevice, S(stream));
+  if (n_table > 0) cudaMemcpyAsync(d_table, table, sizeof(double) * n_table, cudaMemcpyHostToDevice, S(stream));
+  cudaMemsetAsync(map, 0, sizeof(int16_t) * (size_t)tot_rows * tot_cols, S(stream));
+  const int px = d->width_px * d->length_px;
+  terrain_raster_kernel<<<dim3(n_tiles, (px + 255) / 256 > 8 ? 8 : (px + 255) / 256), 256, 0, S(stream)>>>(
+      d_tiles, d_table, d->width_px, d->length_px, d->border_px, tot_cols, map);
+  const double hs = d->horizontal_scale;                       // window of terrain.py:166-169
+  const int wx1 = (int)((d->env_length / 2. - 1) / hs), wx2 = (int)((d->env_length / 2. + 1) / hs);
+  const int wy1 = (int)((d->env_width / 2. - 1) / hs), wy2 = (int)((d->env_width / 2. + 1) / hs);
+  terrain_origins_kernel<<<n_tiles, 32, 0, S(stream)>>>(d_tiles, map, d->width_px, d->length_px, d->border_px, tot_cols,
+                                                        d->num_cols, d->env_length, d->env_width, wx1, wx2, wy1, wy2,
+                                                        d->vertical_scale, origins);
+  e = cudaGetLastError();
+  cudaStreamSynchronize(S(stream));                            // one-time init: the staging buffers go away here
+  cudaFree(d_tiles); cudaFree(d_table);
+  if (e != cudaSuccess) return fail((int)e, "terrain kernels: %s", cudaGetErrorString(e));
   return SHIFU_OK;
 }
 

@@ -220,7 +220,9 @@ class TerrainGymEnv(IsaacGymEnv):
         tc = self.cfg.terrain
         if tc.mesh_type not in ('heightfield', 'trimesh'):
             raise NotImplementedError("cfg.terrain.mesh_type must be one of heightfield or trimesh")
-        self.terrain = Terrain(tc, self.num_envs)
+        # cfg.terrain.generator = "device": the map is rasterised by shifu_terrain_generate (row N3)
+        on_device = getattr(tc, "generator", "host") == "device" and str(self.device).startswith("cuda")
+        self.terrain = Terrain(tc, self.num_envs, device=self.device if on_device else None)
         params = gymapi.HeightFieldParams() if tc.mesh_type == 'heightfield' else gymapi.TriangleMeshParams()
         params.transform.p.x = params.transform.p.y = -tc.border_size
         params.transform.p.z = 0.0
@@ -236,8 +238,11 @@ class TerrainGymEnv(IsaacGymEnv):
             params.nb_triangles = self.terrain.triangles.shape[0]
             self.gym.add_triangle_mesh(self.sim, self.terrain.vertices.flatten(order='C'),
                                        self.terrain.triangles.flatten(order='C'), params)
-        self.height_samples = torch.tensor(self.terrain.heightsamples).view(
-            self.terrain.tot_rows, self.terrain.tot_cols).to(self.device)
+        if self.terrain.device_map is not None:
+            self.height_samples = self.terrain.device_map           # built on the device: no upload
+        else:
+            self.height_samples = torch.tensor(self.terrain.heightsamples).view(
+                self.terrain.tot_rows, self.terrain.tot_cols).to(self.device)
         # spawn origins (isaac_gym.py:336-347); terrain type from the GLOBAL env index so that a
         # sharded run reproduces the single-process assignment
         max_init = tc.max_init_terrain_level if tc.curriculum else tc.num_rows - 1

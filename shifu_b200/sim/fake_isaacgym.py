@@ -692,7 +692,8 @@ def _build_modules():
     terr = types.ModuleType("isaacgym.terrain_utils")
     from . import synthetic_terrain as _st
     for name in ("SubTerrain", "pyramid_sloped_terrain", "random_uniform_terrain", "pyramid_stairs_terrain",
-                 "discrete_obstacles_terrain", "stepping_stones_terrain", "convert_heightfield_to_trimesh"):
+                 "discrete_obstacles_terrain", "stepping_stones_terrain", "convert_heightfield_to_trimesh",
+                 "pyramid_params", "random_uniform_params", "stairs_params", "obstacles_params", "stones_params"):
         setattr(terr, name, getattr(_st, name))
 
     pkg.gymapi, pkg.gymtorch, pkg.gymutil = gymapi, gymtorch, gymutil

@@ -121,6 +121,61 @@ def stepping_stones_terrain(terrain, stone_size, stone_distance, max_height, pla
     return terrain
 
 
+# ---------------------------------------------------------------------------------------------
+# Parameter-only twins of the generators above, for the device rasteriser (shifu_terrain_generate,
+# SURVEY.md 8f row N3): they consume numpy.random in EXACTLY the order of their twin, but return the
+# tile record + the drawn numbers instead of touching pixels — so a device-built map is bit-identical
+# to the host-built one under the same seed.  kind codes = enum ShifuTerrainKind.
+# ---------------------------------------------------------------------------------------------
+
+def pyramid_params(terrain, slope, platform_size):
+    peak = int(slope * (terrain.horizontal_scale / terrain.vertical_scale) * (terrain.width / 2))
+    return [peak, int(platform_size / terrain.horizontal_scale / 2)]
+
+
+def random_uniform_params(terrain, min_height, max_height, step=1.0, downsampled_scale=None):
+    if downsampled_scale is None:
+        downsampled_scale = terrain.horizontal_scale
+    lo = int(min_height / terrain.vertical_scale)
+    hi = int(max_height / terrain.vertical_scale)
+    st = max(int(step / terrain.vertical_scale), 1)
+    levels = np.arange(lo, hi + st, st)
+    nx = max(int(terrain.width * terrain.horizontal_scale / downsampled_scale), 2)
+    ny = max(int(terrain.length * terrain.horizontal_scale / downsampled_scale), 2)
+    coarse = np.random.choice(levels, (nx, ny)).astype(np.float64)
+    return nx, ny, coarse.reshape(-1)
+
+
+def stairs_params(terrain, step_width, step_height, platform_size):
+    return [max(int(step_width / terrain.horizontal_scale), 1), int(step_height / terrain.vertical_scale),
+            int(platform_size / terrain.horizontal_scale)]
+
+
+def obstacles_params(terrain, max_height, min_size, max_size, num_rects, platform_size):
+    mh = int(max_height / terrain.vertical_scale)
+    lo = int(min_size / terrain.horizontal_scale)
+    hi = int(max_size / terrain.horizontal_scale)
+    heights = [-mh, -mh // 2, mh // 2, mh]
+    rects = []
+    for _ in range(num_rects):
+        w = np.random.choice(np.arange(lo, hi, 4))
+        l = np.random.choice(np.arange(lo, hi, 4))
+        sx = np.random.choice(np.arange(0, terrain.width - w, 4))
+        sy = np.random.choice(np.arange(0, terrain.length - l, 4))
+        rects += [sx, sy, w, l, np.random.choice(heights)]
+    return [num_rects, int(platform_size / terrain.horizontal_scale)], np.asarray(rects, dtype=np.float64)
+
+
+def stones_params(terrain, stone_size, stone_distance, max_height, platform_size, depth=-10):
+    ss = max(int(stone_size / terrain.horizontal_scale), 1)
+    sd = max(int(stone_distance / terrain.horizontal_scale), 1)
+    mh = int(max_height / terrain.vertical_scale)
+    heights = [np.random.randint(-mh - 1, mh + 1) if mh else 0
+               for _ in range(0, terrain.width, ss + sd) for _ in range(0, terrain.length, ss + sd)]
+    return [ss, sd, int(platform_size / terrain.horizontal_scale), int(depth / terrain.vertical_scale)], \
+        np.asarray(heights, dtype=np.float64)
+
+
 def convert_heightfield_to_trimesh(height_field_raw, horizontal_scale, vertical_scale, slope_threshold=None):
     """The fake simulator never collides against the mesh; hand back an empty one."""
     return np.zeros((0, 3), dtype=np.float32), np.zeros((0, 3), dtype=np.uint32)
