@@ -7,7 +7,7 @@ tree.  Every function cites the reference lines it follows
 parity target named by BASELINE.json is "the reference's own torch
 implementation ... on torch CPU", and using the same aten ops in the same order
 makes this restatement bit-identical to the unmodified reference
-(checked by ``tests/test_oracle_vs_reference.py`` in the build container and
+(checked by ``tests/test_oracle_cpu.py`` in the build container and
 through the committed fixtures under ``tests/golden/`` everywhere else).
 
 PARITY PINNING: the reference ships **no** tests, golden vectors or fixtures for

@@ -178,7 +178,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         try:
             _build.build()
         except Exception as exc:      # pragma: no cover - surfaced with context
-            if not os.path.exists(path):
+            # never run stale kernels against new headers / bindings: a failed rebuild is fatal unless
+            # the existing library was built from exactly these sources
+            if not os.path.exists(path) or _build.needs_build():
                 raise ShifuNativeError(E_STATE, f"cannot build {path}: {exc}") from exc
     if not os.path.exists(path):
         raise ShifuNativeError(E_STATE, f"{path} not found; run `python -m shifu_b200.build` "

@@ -350,8 +350,9 @@ extern "C" int shifu_set_height_map(ShifuCtx* c, const int16_t* hs, int32_t rows
 extern "C" int shifu_set_level_sum(ShifuCtx* c, const int64_t* levels, void* stream) {
   REQUIRE_PTR(c); REQUIRE_PTR(levels);
   if (!c->is_a1) return fail(SHIFU_E_STATE, "terrain levels only apply to an A1 ctx");
-  level_sum_kernel<<<1, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(levels), c->a1.num_envs,
-                                             c->d_stats + SHIFU_NUM_STATS);
+  CUDA_TRY(cudaMemsetAsync(c->d_stats + SHIFU_NUM_STATS, 0, sizeof(double), S(stream)));
+  level_sum_kernel<<<grid_for(c->a1.num_envs, 256, c->sm_count, 2), 256, 0, S(stream)>>>(
+      reinterpret_cast<const long long*>(levels), c->a1.num_envs, c->d_stats + SHIFU_NUM_STATS);
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;
 }

@@ -185,18 +185,18 @@ __global__ void publish_extras_kernel(const double* __restrict__ stats, float* _
   extras[i] = v;
 }
 
-__global__ void level_sum_kernel(const long long* __restrict__ levels, int n, double* __restrict__ out) {
-  // single CTA; called once at set-up
+// set-up only (shifu_set_level_sum): grid-stride sum of the terrain levels; *out must be zeroed first
+__global__ void __launch_bounds__(256) level_sum_kernel(const long long* __restrict__ levels, int n, double* __restrict__ out) {
   __shared__ double s[256];
   double a = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) a += (double)levels[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a += (double)levels[i];
   s[threadIdx.x] = a;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = s[0];
+  if (threadIdx.x == 0) atomicAdd(out, s[0]);       // integer-valued partial sums: exact in any order
 }
 
 }  // namespace shifu

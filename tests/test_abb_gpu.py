@@ -121,8 +121,15 @@ def _arm_ik_check(d, meta, mode, ref32=None):
     assert torch.isfinite(got).all()
     err_ref = float((o32.double() - o64).abs().max())
     err_cuda = float((got.double() - o64).abs().max())
+    # the reference inverts J J^T + l^2 I with LAPACK (torch.inverse) in fp32, the kernel solves by Cholesky:
+    # both are fp32 roundings of the float64 answer, so the bar is "no farther from float64 than the
+    # reference itself" (x2), and the achieved numbers are printed for the record (pytest -s / -rP)
+    err_vs_ref = float((got - o32).abs().max())
+    rel = float(((got.double() - o64).abs() / o64.abs().clamp_min(1e-3)).max())
+    print(f"arm_ik[{mode}]: |cuda - f64| max {err_cuda:.3e} (reference fp32: {err_ref:.3e}), |cuda - ref32| max "
+          f"{err_vs_ref:.3e}, max rel vs f64 {rel:.3e}")
     assert err_cuda <= max(2.0 * err_ref, 1e-6), (mode, err_cuda, err_ref)
-    assert float((got - o32).abs().max()) <= 3.0 * err_ref + 1e-6
+    assert err_vs_ref <= 3.0 * err_ref + 1e-6
     if ref32 is not None:
         assert float((got - torch.from_numpy(ref32)).abs().max()) <= 3.0 * err_ref + 1e-6
 
