@@ -391,6 +391,12 @@ int shifu_terrain_generate(ShifuCtx* ctx, const ShifuTerrainDesc* desc, const Sh
  * stats_out (sum over ranks; the host layer does it with torch.distributed over NCCL — the only
  * collective on the path). */
 int shifu_collect_stats(ShifuCtx* ctx, double* stats_out, int64_t* step_dev_to_advance, void* stream);
+/* Same, into slot `slot` of a ring double[slots][SHIFU_NUM_STATS] (slot < 0: *step_dev % slots, read
+ * before the increment): every step owns its vector, so a sharded run can all-reduce step t on a side
+ * stream while step t+1 already runs ("overlap it on a side stream so it never gates the
+ * next step"), also for steps replayed from a CUDA graph. */
+int shifu_collect_stats_ring(ShifuCtx* ctx, double* ring, int32_t slots, int32_t slot, int64_t* step_dev_to_advance,
+                             void* stream);
 
 /* extras["episode"][term k] = mean over reset envs / max_episode_length_s, terrain_levels mean,
  * success_rate; values are left unchanged when no env reset this step (env.py:115-116).
@@ -401,7 +407,8 @@ int shifu_publish_extras(ShifuCtx* ctx, const double* stats, float* extras_out, 
  * gets its own array, so the extras dicts of earlier steps that a caller still holds (rsl_rl keeps one
  * per rollout step; the reference allocates fresh tensors on every resetting step, env.py:124-130)
  * are not overwritten; a step without resets copies the previous slot.  slot < 0: the slot is
- * (*step_dev - 1) % slots, for graph-replayed steps whose counter lives on the device. */
+ * (*step_dev - 1) % slots, for graph-replayed steps whose counter lives on the device, and `stats` is
+ * then the ring base shifu_collect_stats_ring wrote (same slot). */
 int shifu_publish_extras_ring(ShifuCtx* ctx, const double* stats, float* ring, int32_t slots, int32_t slot,
                               const int64_t* step_dev, void* stream);
 

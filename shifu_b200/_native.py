@@ -151,6 +151,7 @@ SIGNATURES = {
     "shifu_a1_reset_idx": [_VP, C.POINTER(A1StepIO), _VP, _I32, _VP],
     "shifu_abb_reset_idx": [_VP, C.POINTER(AbbStepIO), _VP, _I32, _VP],
     "shifu_collect_stats": [_VP, _VP, _VP, _VP],
+    "shifu_collect_stats_ring": [_VP, _VP, _I32, _I32, _VP, _VP],
     "shifu_publish_extras": [_VP, _VP, _VP, _VP],
     "shifu_publish_extras_ring": [_VP, _VP, _VP, _I32, _I32, _VP, _VP],
     "shifu_read_stats_host": [_VP, _VP, _VP],

@@ -599,7 +599,18 @@ extern "C" int shifu_a1_reset_idx(ShifuCtx* c, const ShifuA1StepIO* io, const in
 extern "C" int shifu_collect_stats(ShifuCtx* c, double* out, int64_t* step_dev, void* stream) {
   REQUIRE_PTR(c); REQUIRE_PTR(out);
   const double n = c->is_a1 ? c->a1.num_envs : c->abb.num_envs;
-  collect_stats_kernel<<<1, 32, 0, S(stream)>>>(c->d_stats, c->d_stats + SHIFU_NUM_STATS, out, n,
+  collect_stats_kernel<<<1, 32, 0, S(stream)>>>(c->d_stats, c->d_stats + SHIFU_NUM_STATS, out, 1, 0, n,
+                                                reinterpret_cast<long long*>(step_dev));
+  CUDA_TRY(cudaGetLastError());
+  return SHIFU_OK;
+}
+
+extern "C" int shifu_collect_stats_ring(ShifuCtx* c, double* ring, int32_t slots, int32_t slot, int64_t* step_dev, void* stream) {
+  REQUIRE_PTR(c); REQUIRE_PTR(ring);
+  if (slots < 1 || slot >= slots) return fail(SHIFU_E_RANGE, "slot %d outside the ring of %d", slot, slots);
+  if (slot < 0 && step_dev == nullptr) return fail(SHIFU_E_NULL, "slot < 0 needs the device step counter");
+  const double n = c->is_a1 ? c->a1.num_envs : c->abb.num_envs;
+  collect_stats_kernel<<<1, 32, 0, S(stream)>>>(c->d_stats, c->d_stats + SHIFU_NUM_STATS, ring, slots, slot, n,
                                                 reinterpret_cast<long long*>(step_dev));
   CUDA_TRY(cudaGetLastError());
   return SHIFU_OK;

@@ -140,10 +140,15 @@ __global__ void clip_kernel(const float* __restrict__ in, float* __restrict__ ou
 // Step statistics.  acc[] is what the post-physics kernels atomically add into during a step;
 // collect moves it out (adding the persistent all-env terrain-level sum and N) and clears it.
 // ------------------------------------------------------------------------------------------
+// `out` is slot `slot` of a ring of `slots` vectors (slot < 0: *step_dev % slots, read before the
+// increment, for graph-replayed steps); slots == 1 is the plain single-vector form.
 __global__ void collect_stats_kernel(double* __restrict__ acc, double* __restrict__ level_sum,
-                                     double* __restrict__ out, double n_envs, long long* step_dev) {
+                                     double* __restrict__ out, int slots, int slot, double n_envs, long long* step_dev) {
   const int i = threadIdx.x;
+  if (slot < 0) slot = (int)(*step_dev % slots);
+  __syncwarp();
   if (i == 31 && step_dev != nullptr) *step_dev += 1;      // common_step_counter += 1 (env.py:96)
+  out += (size_t)slot * SHIFU_NUM_STATS;
   if (i >= SHIFU_NUM_STATS) return;
   double v = acc[i];
   acc[i] = 0.0;
@@ -166,7 +171,10 @@ __global__ void publish_extras_kernel(const double* __restrict__ stats, float* _
                                       const long long* __restrict__ step_dev, float max_len_s, int n_terms) {
   const int i = threadIdx.x;
   if (i >= SHIFU_NUM_STATS) return;
-  if (slot < 0) slot = (int)((*step_dev - 1) % slots);
+  if (slot < 0) {                       // graph-replayed step: `stats` is the ring shifu_collect_stats_ring fills
+    slot = (int)((*step_dev - 1) % slots);
+    stats += (size_t)slot * SHIFU_NUM_STATS;
+  }
   const int prev = (slot + slots - 1) % slots;
   float* extras = ring + (size_t)slot * SHIFU_NUM_STATS;
   const float* old = ring + (size_t)prev * SHIFU_NUM_STATS;

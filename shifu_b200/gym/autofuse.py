@@ -219,10 +219,11 @@ def bind_a1(env, hp):
 
 def _resident_state(env) -> bool:
     """True when nothing runs between the kernel launches of a step: the stand-in simulator with no
-    snapshot provider (state resident in HBM, refresh calls are no-ops) and no cross-rank collective."""
+    snapshot provider (state resident in HBM, refresh calls are no-ops).  A cross-rank collective is
+    fine: it runs after the replay, on the side stream."""
     sim = env.isg_env.sim
-    return (getattr(sim, "provider", 0) is None and env.stats_allreduce is None
-            and not getattr(env.isg_env.gym, "needs_indexed_resets", True) and getattr(env, "use_cuda_graph", True))
+    return (getattr(sim, "provider", 0) is None and not getattr(env.isg_env.gym, "needs_indexed_resets", True)
+            and getattr(env, "use_cuda_graph", True))
 
 
 def a1_fused_step(env, hp, actions: torch.Tensor):
@@ -234,7 +235,7 @@ def a1_fused_step(env, hp, actions: torch.Tensor):
     env.common_step_counter += 1
     hp.step_counter = env.common_step_counter - 1
     if _resident_state(env):
-        hp.graph_step(actions, isg.decimation)
+        hp.graph_step(actions, isg.decimation, allreduce=env.stats_allreduce)
         env.extras.update(hp.extras())
         return env.obs_buf, env.privileged_obs_buf, env.rew_buf, env.reset_buf, env.extras
     for i in range(isg.decimation):

@@ -245,6 +245,7 @@ class _StepStats:
         self._stats_slot = 0
         self._side = None
         self._pending = None
+        self._slot_events = {}
 
     @property
     def slot(self) -> int:
@@ -259,26 +260,40 @@ class _StepStats:
         return self.extras_ring[self.slot]
 
     def wait_stats(self):
-        """Main stream waits for the side-stream all-reduce + publish of the previous step."""
+        """Main stream waits for the side-stream all-reduce + publish still in flight (call before reading
+        ``extras`` values of a sharded run on the main stream; single-GPU runs publish in-stream)."""
         if self._pending is not None:
             torch.cuda.current_stream().wait_event(self._pending)
             self._pending = None
 
-    def _finalize_stats(self, allreduce, advance_step_dev: bool):
-        lib, h = self.lib, self.ctx.handle
-        step_dev = nv.ptr(self.step_dev) if advance_step_dev else None
-        if allreduce is None:
-            self._stats_slot = 0
-            st = self.stats_ring[0]
-            nv.check(lib.shifu_collect_stats(h, nv.ptr(st), step_dev, nv.current_stream()))
-            nv.check(lib.shifu_publish_extras_ring(h, nv.ptr(st), nv.ptr(self.extras_ring), EXTRAS_SLOTS,
-                                                   -1 if advance_step_dev else self.slot, nv.ptr(self.step_dev),
+    def _slot_guard(self):
+        """Before a slot of the rings is reused: its side-stream user of EXTRAS_SLOTS steps ago is done."""
+        done = self._slot_events.pop(self.slot, None)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+
+    def _collect(self, advance_step_dev: bool):
+        """Step statistics -> this step's slot of the ring (capturable: the slot can come from the device
+        step counter)."""
+        self._stats_slot = self.slot
+        if not torch.cuda.is_current_stream_capturing():
+            self._slot_guard()
+        nv.check(self.lib.shifu_collect_stats_ring(self.ctx.handle, nv.ptr(self.stats_ring), EXTRAS_SLOTS,
+                                                   -1 if advance_step_dev else self.slot,
+                                                   nv.ptr(self.step_dev) if advance_step_dev else None,
                                                    nv.current_stream()))
-            return
-        self.wait_stats()
-        slot = self._stats_slot = self.slot
+
+    def _publish(self, allreduce, from_step_dev: bool = False):
+        """(all-reduce over ranks ->) extras of this step's slot.  With a collective both run on a side
+        stream: nothing on the main stream waits for them, the next step starts right away; the slot's
+        previous user (EXTRAS_SLOTS steps ago) has long finished."""
+        lib, h, slot = self.lib, self.ctx.handle, self.slot
         st = self.stats_ring[slot]
-        nv.check(lib.shifu_collect_stats(h, nv.ptr(st), step_dev, nv.current_stream()))
+        if allreduce is None:
+            nv.check(lib.shifu_publish_extras_ring(h, nv.ptr(self.stats_ring) if from_step_dev else nv.ptr(st),
+                                                   nv.ptr(self.extras_ring), EXTRAS_SLOTS, -1 if from_step_dev else slot,
+                                                   nv.ptr(self.step_dev), nv.current_stream()))
+            return
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
         self._side.wait_stream(torch.cuda.current_stream())
@@ -288,6 +303,11 @@ class _StepStats:
                                                    nv.current_stream()))
             self._pending = torch.cuda.Event()
             self._pending.record(self._side)
+            self._slot_events[slot] = self._pending
+
+    def _finalize_stats(self, allreduce, advance_step_dev: bool):
+        self._collect(advance_step_dev)
+        self._publish(allreduce, from_step_dev=advance_step_dev)
 
 
 class HeightScan:
@@ -429,7 +449,6 @@ class A1HotPath(_StepStats):
         """Row a2 (+a1 when ``raw_actions`` is given: env.actions = clip(0.5*a, +-1) is produced too)."""
         s = nv.current_stream()
         if raw_actions is not None:
-            self.wait_stats()
             nv.check(self.lib.shifu_pd_torque(self.ctx.handle, nv.ptr(raw_actions), nv.ptr(self.actions),
                                               nv.ptr(self.dof_state), nv.ptr(self.torques), s))
         else:
@@ -482,7 +501,7 @@ class A1HotPath(_StepStats):
 
     # -- the whole control step without a simulator in between (bench / graph capture) ------
     def step_resident(self, raw_actions: torch.Tensor, decimation: int = 4, use_step_dev: bool = False,
-                      allreduce=None):
+                      allreduce=None, publish: bool = True):
         """PD x decimation, (body-frame unless carried), fused post-physics, compaction, stats —
         on whatever the flat state tensors currently hold."""
         self.pd_torque(raw_actions)
@@ -491,19 +510,23 @@ class A1HotPath(_StepStats):
         if not self.carry_body_frame:
             self.body_frame()
         self.post_physics(use_step_dev)
-        self.finalize(allreduce, advance_step_dev=use_step_dev)
+        self.compact()
+        self._collect(use_step_dev)
+        if publish:
+            self._publish(allreduce, from_step_dev=use_step_dev)
 
     # -- the same step as ONE CUDA-graph replay (launch-bound small-N configurations) -----------
-    def graph_step(self, raw_actions: torch.Tensor, decimation: int = 4):
+    def graph_step(self, raw_actions: torch.Tensor, decimation: int = 4, allreduce=None):
         """``step_resident`` captured once and replayed: PD x decimation, (body frame), fused post-physics,
         compaction, statistics and extras publish cost one graph launch instead of 8-9 kernel launches
-        (52 -> ~25 us per step at 4 096 envs).  Only valid when nothing has to run between the launches
-        (resident state: no simulator crossing, no collective).  The Philox step counter lives on the
-        device (``step_dev``) and is advanced inside the graph."""
+        (52 -> ~20 us per step at 4 096 envs).  Only valid when nothing has to run between the launches
+        (resident state: no simulator crossing).  The Philox step counter lives on the device
+        (``step_dev``) and is advanced inside the graph.  In a sharded run the graph ends with the
+        statistics collect; the all-reduce and the publish follow on the side stream."""
         if self._graph is None:
             if self._graph_warm < 2:                     # first launches outside capture (module loading)
                 self._graph_warm += 1
-                return self.step_resident(raw_actions, decimation)
+                return self.step_resident(raw_actions, decimation, allreduce=allreduce)
             if self._graph_actions is None:
                 self._graph_actions = torch.empty_like(raw_actions)
             if raw_actions.data_ptr() != self._graph_actions.data_ptr():
@@ -513,19 +536,24 @@ class A1HotPath(_StepStats):
             graph = torch.cuda.CUDAGraph()
             before = self.step_counter
             with torch.cuda.graph(graph):
-                self.step_resident(self._graph_actions, decimation, use_step_dev=True)
+                self.step_resident(self._graph_actions, decimation, use_step_dev=True, publish=allreduce is None)
             self.step_counter = before                   # capture recorded the launches without running them
             self._graph, self._graph_decimation, self._dev_step = graph, decimation, before + 1
-        if decimation != self._graph_decimation or raw_actions.shape != self._graph_actions.shape:
-            raise ValueError("graph_step was captured for another decimation / action shape")
+            self._graph_publishes = allreduce is None
+        if decimation != self._graph_decimation or raw_actions.shape != self._graph_actions.shape or \
+                self._graph_publishes != (allreduce is None):
+            raise ValueError("graph_step was captured for another decimation / action shape / collective mode")
         if self._dev_step != self.step_counter + 1:      # eager steps or resets ran in between
             self.step_dev.fill_(self.step_counter + 1)
         if raw_actions.data_ptr() != self._graph_actions.data_ptr():   # callers that write into
             self._graph_actions.copy_(raw_actions)                       # action_input() skip this copy
         self.step_counter += 1
-        self._stats_slot = 0
+        self._stats_slot = self.slot
+        self._slot_guard()
         self._graph.replay()
         self._dev_step = self.step_counter + 1
+        if allreduce is not None:
+            self._publish(allreduce)
 
     def action_input(self) -> torch.Tensor:
         """The (N, 12) buffer the captured step reads its raw actions from: a policy that writes its
