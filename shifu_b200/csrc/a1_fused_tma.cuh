@@ -1,26 +1,31 @@
-// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs (3 per SM) with
-// three warp roles that never meet at a CTA-wide barrier —
+// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs (2 per SM, 480 threads)
+// with three warp roles that never meet at a CTA-wide barrier —
 //
 //   DMA warp (1 lane)    bulk-TMA loads (cp.async.bulk -> mbarrier, SASS UBLKCP) of everything the
 //                        tile reads — the root / dof / contact / history / torque / action rows
 //                        and the per-env scalars (ep_len, command, carried velocities, episode
-//                        sums, env origin, terrain level / type) — into a double-buffered
-//                        shared-memory stage, refilled as soon as the tile's head phase is over;
+//                        sums, env origin, terrain level / type) — into a ring of three
+//                        shared-memory stages, refilled as soon as the tile's head phase is over;
 //                        bulk-TMA store of the pushed history tile
-//   B group (2 warps; lane = env; V3_B_GROUPS_CFG groups, one by default)
-//                        termination, the reward-term list + episode sums, reset (curriculum,
-//                        Philox draws, state rewrite), per-step log sums — the scalar game logic
-//                        of ShifuVecEnv.post_step (env.py:93-106); reads only the stage, so it
-//                        issues no global loads of its own
-//   scan group (6 warps; thread = scan point)
-//                        obs head from the post-reset rows (a1_conditional.py:131-144), history
-//                        push (train.py:12-14), carried body-frame velocities, then the 187-point
-//                        height scan of every env of the tile (isaac_gym.py:393-433) in batches of
-//                        8 envs with packed fp32x2 arithmetic, streamed to HBM with st.global.cs
+//   B group (2 warps; lane = env)
+//                        yaw normalisation for the scan (first: the scan group starts on e_done),
+//                        the reward-term list (split over both warps by a host-side cost balance) +
+//                        episode sums, termination, reset (curriculum, Philox draws, state rewrite —
+//                        warp 1, while warp 0 does the ordered accumulation and the flags), per-step
+//                        log sums — the scalar game logic of ShifuVecEnv.post_step (env.py:93-106);
+//                        reads only the stage, so it issues no global loads of its own
+//   scan group (12 warps; thread = scan point, warp w: points 32*(w%6).., env batches 2*(w/6), +1)
+//                        first item's index arithmetic + gathers, then the obs head from the
+//                        post-reset rows (a1_conditional.py:131-144), history push (train.py:12-14),
+//                        carried body-frame velocities, then the rest of the 187-point height scan
+//                        (isaac_gym.py:393-433) in batches of 8 envs with packed fp32x2 arithmetic,
+//                        streamed to HBM with st.global.cs (-DV3_OBS_TMA: staged in shared memory
+//                        and written as 8-row bulk copies instead; measured 1 % slower)
 //
 // mbarriers hand a stage round DMA -> B -> scan -> DMA; every thread of the producing group
 // arrives itself, so fast warps never wait for slow siblings.  The per-env scalars the scan needs
 // travel through a 4-deep ring, which lets the B group run ahead of the scan group.
+// (V3_SCAN_WARPS=6 / V3_CTAS_CFG=3 / V3_STAGES_CFG=2 rebuilds round 1's 3-CTA shape.)
 #pragma once
 #include "a1_fused.cuh"
 #include "f32x2.cuh"

@@ -161,7 +161,8 @@ def fuse_a1(env, carry_body_frame: bool = True, rng_seed: int = 0x5EED):
     hp = hotpath.A1HotPath(desc, root_state=isg.root_state, dof_state=isg.dof_state, contact_state=isg.contact_state,
                            height_samples=isg.height_samples, terrain_origins=isg.terrain_origins,
                            terrain_types=isg.terrain_types, env_origins=isg.env_origins, terms=names,
-                           carry_body_frame=carry_body_frame)
+                           carry_body_frame=carry_body_frame,
+                           want_measured_heights=bool(getattr(cfg, "store_measured_heights", False)))
     # the probes below run the user's hooks on the env's CURRENT tensors: point the hot path at them
     hp.adopt(actions=env.actions, history=env.actions_recorder.history_buf, command=env.command_buf,
              torques=rb.torques, base_lin_vel=rb.base_lin_vel, base_ang_vel=rb.base_ang_vel,
@@ -179,7 +180,7 @@ def _check_a1_obs_and_termination(env):
     rb, isg = env.robot, env.isg_env
     with terms.A1Probe(env) as pr:
         pr.randomize(4321)
-        had = getattr(isg, "measured_heights", None)
+        had = isg.__dict__.get("_measured_heights")
         isg.measured_heights = torch.randn(env.num_envs, isg.num_height_points, device=env.device)
         try:
             env.compute_observations()
@@ -213,7 +214,8 @@ def bind_a1(env, hp):
     rb.torques, rb.dof_targets, rb.rand_force_buf = hp.torques, hp.dof_targets, hp.rand_force
     rb.base_lin_vel, rb.base_ang_vel = hp.base_lin_vel, hp.base_ang_vel
     rb.projected_gravity, rb.gravity_vec = hp.projected_gravity, hp.gravity_vec
-    isg.measured_heights = hp.measured_heights
+    isg.measured_heights = hp.measured_heights          # None unless cfg.store_measured_heights: filled on demand
+    isg.__dict__["_heights_on_demand"] = hp.measured_heights is None
     env.extras.update(hp.extras())
 
 

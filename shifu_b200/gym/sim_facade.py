@@ -214,6 +214,25 @@ class TerrainGymEnv(IsaacGymEnv):
         if self.cfg.terrain.measure_heights:
             self.measured_heights = self.get_heights()
 
+    # ``measured_heights`` (isaac_gym.py:320-322) is a plain attribute in user-hook mode.  A fused task
+    # consumes the heights inside the kernel; unless it is asked to keep them (``store_measured_heights``,
+    # +748 B/env written per step) the attribute is filled on demand by the stand-alone scan over the
+    # CURRENT root rows — identical for every env that did not reset in the last step.
+    @property
+    def measured_heights(self):
+        kept = self.__dict__.get("_measured_heights")
+        if kept is None and self.__dict__.get("_heights_on_demand", False):
+            return self.get_heights()
+        return kept
+
+    @measured_heights.setter
+    def measured_heights(self, value):
+        self.__dict__["_measured_heights"] = value
+
+    @measured_heights.deleter
+    def measured_heights(self):
+        self.__dict__.pop("_measured_heights", None)
+
     def create_ground(self):
         assert isinstance(self.cfg, TerrainEnvConfig), "cfg must be a TerrainEnvConfig"
         self.up_axis_idx = 2

@@ -130,7 +130,7 @@ class A1Conditional(ShifuVecEnv):
              "torques_penalize")
 
     def __init__(self, cfg, fused: bool = True, carry_body_frame: bool = True, rng_seed: int = 0x5EED,
-                 env_offset: int = 0, num_envs_global: int = None, store_measured_heights: bool = True,
+                 env_offset: int = 0, num_envs_global: int = None, store_measured_heights: bool = False,
                  use_cuda_graph: bool = True):
         super().__init__(cfg, env_offset=env_offset, num_envs_global=num_envs_global)
         self.auto_fuse = False          # this class wires its own fusion (explicit fused= switch)
@@ -192,7 +192,8 @@ class A1Conditional(ShifuVecEnv):
         rb.torques, rb.dof_targets, rb.rand_force_buf = hp.torques, hp.dof_targets, hp.rand_force
         rb.base_lin_vel, rb.base_ang_vel = hp.base_lin_vel, hp.base_ang_vel
         rb.projected_gravity, rb.gravity_vec = hp.projected_gravity, hp.gravity_vec
-        isg.measured_heights = hp.measured_heights
+        isg.measured_heights = hp.measured_heights      # None unless store_measured_heights: filled on demand
+        isg.__dict__["_heights_on_demand"] = hp.measured_heights is None
         self.extras = hp.extras()
         hp.body_frame()
 

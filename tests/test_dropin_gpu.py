@@ -94,6 +94,7 @@ def test_reference_a1_conditional_replays_golden(fuse):
     cfg.num_envs, cfg.device = n, "cuda:0"
     cfg.rng_seed = meta["rng_seed"]
     cfg.carry_body_frame = False
+    cfg.store_measured_heights = True          # the fixture compares measured_heights of resetting envs too
     for k, v in meta["terrain"].items():
         setattr(cfg.terrain, k, v)
     np.random.seed(0)

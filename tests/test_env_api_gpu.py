@@ -28,7 +28,7 @@ def _make_a1(n, terrain, fused=True, carry=False):
         setattr(cfg.terrain, k, v)
     np.random.seed(0)
     torch.manual_seed(0)
-    return A1Conditional(cfg, fused=fused, carry_body_frame=carry)
+    return A1Conditional(cfg, fused=fused, carry_body_frame=carry, store_measured_heights=True)
 
 
 def _env_outputs(env):
