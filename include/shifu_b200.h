@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHIFU_ABI_VERSION 1
+#define SHIFU_ABI_VERSION 2
 
 #define SHIFU_MAX_DOF 12
 #define SHIFU_MAX_LEG_BODIES 8
@@ -67,7 +67,11 @@ enum ShifuRewardTerm {
   SHIFU_REW_DOF_VEL = 11,         /* p0*|qd|^2                        sum(square(dof_vel)) */
   SHIFU_REW_ACTION_RATE = 12,     /* p0*|a_{t-1} - a_t|^2             sum(square(actions_recorder.get_last(0) - actions)) */
   SHIFU_REW_BASE_HEIGHT = 13,     /* p0*(z - p1)^2                    square(base_pose[:, 2] - p1) */
-  SHIFU_REW_COUNT = 14
+  SHIFU_REW_DOF_POS_LIMITS = 14,  /* p0*sum(-(q - lo).clip(max=0) + (q - hi).clip(min=0))   lo/hi = dof_pos_limit_low/high */
+  SHIFU_REW_FEET_AIR_TIME = 15,   /* p0*sum((air_time + dt - p1) * first_contact) * [|cmd_xy| > air_time_cmd_min];
+                                     STATEFUL: swing_time / last_contacts (a1_conditional.py:100-103) are
+                                     updated exactly like legged_gym's _reward_feet_air_time */
+  SHIFU_REW_COUNT = 16
 };
 
 /* Index of each statistic in the stats vector (double[SHIFU_NUM_STATS]) that
@@ -135,6 +139,15 @@ typedef struct ShifuA1Desc {
   int32_t num_reward_terms;
   int32_t reward_terms[SHIFU_MAX_REWARD_TERMS];     /* enum ShifuRewardTerm, list order */
   float reward_params[SHIFU_MAX_REWARD_TERMS][2];   /* (p0, p1) per listed term */
+  /* constants of the row-N1 terms that need more than (p0, p1) */
+  float dof_pos_limit_low[SHIFU_MAX_DOF];           /* robot.dof_lower_limits (robot.py:35-45) */
+  float dof_pos_limit_high[SHIFU_MAX_DOF];
+  int32_t num_feet;                                 /* <= 4 */
+  int32_t feet_bodies[4];                           /* robot.ee_indices (end_effector_names, task_config.py:21) */
+  float feet_contact_force;                         /* a foot touches when F_z > this (1.0) */
+  float air_time_cmd_min;                           /* term is 0 unless |cmd_xy| > this (0.1) */
+  float air_time_dt;                                /* control dt added to swing_time every step (isaac_gym.py:26) */
+  int32_t air_time_reset;                           /* !=0: reset_idx zeroes swing_time / last_contacts of the env */
 } ShifuA1Desc;
 
 /* Tensors of one A1 step.  "rw" = read and written in place. */
@@ -167,6 +180,8 @@ typedef struct ShifuA1StepIO {
   const int64_t* step_dev;        /* optional: when non-NULL the step is read from this device word
                                      instead (lets a captured CUDA graph replay with a moving
                                      counter; shifu_collect_stats can advance it) */
+  float* swing_time;              /* rw (N, num_feet), only read when SHIFU_REW_FEET_AIR_TIME is listed (may be NULL otherwise) */
+  uint8_t* last_contacts;         /* rw (N, num_feet) bool, same */
   int32_t carry_body_frame;      /* !=0: also write next step's base_lin/ang_vel, projected_gravity
                                      from the post-reset root row (== LeggedRobot.post_step of the
                                      next control step, robot.py:222-229, as long as nobody else

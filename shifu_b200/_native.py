@@ -12,12 +12,13 @@ import os
 from typing import Optional
 
 MAX_DOF, MAX_LEG, MAX_PX, MAX_PY, MAX_TERMS, NUM_STATS = 12, 8, 17, 11, 8, 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enum ShifuRewardTerm
 REW_TRACKING_LIN_VEL, REW_TRACKING_ANG_VEL, REW_STABILIZING_BASE, REW_SMOOTHING_ACTION = 0, 1, 2, 3
 REW_LEG_COLLISION, REW_TORQUES, REW_ABB_REACHING, REW_ABB_SUCCESS = 4, 5, 6, 7
 REW_LIN_VEL_Z, REW_ANG_VEL_XY, REW_ORIENTATION, REW_DOF_VEL, REW_ACTION_RATE, REW_BASE_HEIGHT = 8, 9, 10, 11, 12, 13
+REW_DOF_POS_LIMITS, REW_FEET_AIR_TIME = 14, 15
 STAT_TERM0, STAT_NRESET, STAT_LEVEL_SUM, STAT_SUCCESS, STAT_NENVS = 0, 8, 9, 10, 11
 
 E_NULL, E_RANGE, E_STATE, E_NODEVICE, E_ALIGN = -1, -2, -3, -4, -5
@@ -51,6 +52,9 @@ class A1Desc(C.Structure):
         ("level_up_distance", C.c_float), ("level_down_factor", C.c_float),
         ("num_reward_terms", C.c_int32), ("reward_terms", C.c_int32 * MAX_TERMS),
         ("reward_params", (C.c_float * 2) * MAX_TERMS),
+        ("dof_pos_limit_low", C.c_float * MAX_DOF), ("dof_pos_limit_high", C.c_float * MAX_DOF),
+        ("num_feet", C.c_int32), ("feet_bodies", C.c_int32 * 4), ("feet_contact_force", C.c_float),
+        ("air_time_cmd_min", C.c_float), ("air_time_dt", C.c_float), ("air_time_reset", C.c_int32),
     ]
 
 
@@ -64,7 +68,8 @@ class A1StepIO(C.Structure):
         ("terrain_origins", C.c_void_p), ("dof_targets", C.c_void_p), ("rand_force", C.c_void_p),
         ("obs_buf", C.c_void_p), ("rew_buf", C.c_void_p), ("reset_buf", C.c_void_p),
         ("time_out_buf", C.c_void_p), ("contact_term_buf", C.c_void_p), ("measured_heights", C.c_void_p),
-        ("step", C.c_int64), ("step_dev", C.c_void_p), ("carry_body_frame", C.c_int32),
+        ("step", C.c_int64), ("step_dev", C.c_void_p), ("swing_time", C.c_void_p), ("last_contacts", C.c_void_p),
+        ("carry_body_frame", C.c_int32),
     ]
 
 

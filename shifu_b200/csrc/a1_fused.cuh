@@ -62,35 +62,67 @@ __device__ __forceinline__ void store_span(float* __restrict__ dst, const float*
 
 // One reward term for env e (lane = env).  a1_conditional.py:162-192; every op rounds like the
 // aten elementwise op it stands for.
-// Terms 8-13 (legged_gym-style, see enum ShifuRewardTerm): pg = this step's projected gravity row.
-__device__ __forceinline__ float a1_extra_term(int code, float p0, float p1, const float* lin, const float* ang,
-                                               const float* pg, const float* dof_row, const float* hist_row,
-                                               const float* act_row, float base_z) {
+// Terms 8-15 (legged_gym-style, see enum ShifuRewardTerm).  Everything a term may read for one env:
+struct TermCtx {
+  const float *cmd, *lin, *ang, *pg;      // command, body-frame velocities, projected gravity (this step's)
+  const float *dof_row, *hist_row, *act_row, *contact_row;
+  float base_z;
+  float* swing;                           // (num_feet) feet-air-time state of the env (global memory), or nullptr
+  unsigned char* last;                    // (num_feet) last_contacts
+};
+
+__device__ __noinline__ float a1_extra_term(int code, float p0, float p1, const A1K& k, const TermCtx& c) {
   switch (code) {
     case SHIFU_REW_LIN_VEL_Z:
-      return mul_rn(p0, mul_rn(lin[2], lin[2]));
+      return mul_rn(p0, mul_rn(c.lin[2], c.lin[2]));
     case SHIFU_REW_ANG_VEL_XY:
-      return mul_rn(p0, add_rn(mul_rn(ang[0], ang[0]), mul_rn(ang[1], ang[1])));
+      return mul_rn(p0, add_rn(mul_rn(c.ang[0], c.ang[0]), mul_rn(c.ang[1], c.ang[1])));
     case SHIFU_REW_ORIENTATION:
-      return mul_rn(p0, add_rn(mul_rn(pg[0], pg[0]), mul_rn(pg[1], pg[1])));
+      return mul_rn(p0, add_rn(mul_rn(c.pg[0], c.pg[0]), mul_rn(c.pg[1], c.pg[1])));
     case SHIFU_REW_DOF_VEL: {
       float acc = 0.0f;
 #pragma unroll
-      for (int d = 0; d < A1_DOF; ++d) acc = add_rn(acc, mul_rn(dof_row[2 * d + 1], dof_row[2 * d + 1]));
+      for (int d = 0; d < A1_DOF; ++d) acc = add_rn(acc, mul_rn(c.dof_row[2 * d + 1], c.dof_row[2 * d + 1]));
       return mul_rn(p0, acc);
     }
     case SHIFU_REW_ACTION_RATE: {
       float acc = 0.0f;
 #pragma unroll
       for (int d = 0; d < A1_DOF; ++d) {
-        const float df = sub_rn(hist_row[d * A1_HIST], act_row[d]);
+        const float df = sub_rn(c.hist_row[d * A1_HIST], c.act_row[d]);
         acc = add_rn(acc, mul_rn(df, df));
       }
       return mul_rn(p0, acc);
     }
     case SHIFU_REW_BASE_HEIGHT: {
-      const float df = sub_rn(base_z, p1);
+      const float df = sub_rn(c.base_z, p1);
       return mul_rn(p0, mul_rn(df, df));
+    }
+    case SHIFU_REW_DOF_POS_LIMITS: {          // -(q - lo).clip(max=0) + (q - hi).clip(min=0), summed over the dofs
+      float acc = 0.0f;
+#pragma unroll
+      for (int d = 0; d < A1_DOF; ++d) {
+        const float q = c.dof_row[2 * d];
+        const float under = -fminf(sub_rn(q, k.dof_lo[d]), 0.0f), over = fmaxf(sub_rn(q, k.dof_hi[d]), 0.0f);
+        acc = add_rn(acc, add_rn(under, over));
+      }
+      return mul_rn(p0, acc);
+    }
+    case SHIFU_REW_FEET_AIR_TIME: {           // legged_gym _reward_feet_air_time on swing_time / last_contacts
+      if (c.swing == nullptr) return 0.0f;
+      float rew = 0.0f;
+      for (int f = 0; f < k.n_feet; ++f) {
+        const bool contact = c.contact_row[k.feet[f] * 3 + 2] > k.feet_thr;
+        const bool filt = contact | (c.last[f] != 0);
+        c.last[f] = contact ? 1 : 0;
+        float air = c.swing[f];
+        const bool first = (air > 0.0f) & filt;
+        air = add_rn(air, k.air_dt);
+        rew = add_rn(rew, first ? sub_rn(air, p1) : 0.0f);
+        c.swing[f] = filt ? 0.0f : air;
+      }
+      const bool moving = norm2_fma(c.cmd[0], c.cmd[1]) > k.air_cmd_min;
+      return mul_rn(p0, moving ? rew : 0.0f);
     }
     default:
       return 0.0f;
@@ -98,10 +130,14 @@ __device__ __forceinline__ float a1_extra_term(int code, float p0, float p1, con
 }
 
 __device__ __noinline__ float a1_eval_term(int code, float p0, float p1, const A1K& k, const A1Smem& s, int e,
-                                           const float* pg) {
+                                           const ShifuA1StepIO& io, long long ge) {
   const float* cla = s.cla[e];
-  if (code >= SHIFU_REW_LIN_VEL_Z)
-    return a1_extra_term(code, p0, p1, cla + 3, cla + 6, pg, s.dof[e], s.hist[e], s.act[e], s.root[e][2]);
+  if (code >= SHIFU_REW_LIN_VEL_Z) {
+    const TermCtx c{cla, cla + 3, cla + 6, io.projected_gravity + ge * 3, s.dof[e], s.hist[e], s.act[e], s.contact[e],
+                    s.root[e][2], io.swing_time ? io.swing_time + ge * k.n_feet : nullptr,
+                    io.last_contacts ? io.last_contacts + ge * k.n_feet : nullptr};
+    return a1_extra_term(code, p0, p1, k, c);
+  }
   switch (code) {
     case SHIFU_REW_TRACKING_LIN_VEL: {
       const float dx = sub_rn(cla[0], cla[3]), dy = sub_rn(cla[1], cla[4]);
@@ -206,8 +242,7 @@ a1_post_physics_kernel(const __grid_constant__ A1K k, const __grid_constant__ Sh
     if (lane_env) {
 #pragma unroll 1
       for (int j = warp; j < k.n_terms; j += A1_THREADS / 32)
-        s.rterm[j][lane] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane,
-                                        io.projected_gravity + (long long)ge * 3);
+        s.rterm[j][lane] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane, io, ge);
       if (warp == 0) {                                                  // a1_conditional.py:146-148
         const float* fb = &s.contact[lane][k.base_body * 3];
         contact_term = norm3_fma(fb[0], fb[1], fb[2]) > k.contact_thr;
@@ -385,8 +420,7 @@ a1_eval_terms_kernel(const __grid_constant__ A1K k, const __grid_constant__ Shif
     __syncthreads();
     if (lane < ne)
       for (int j = warp; j < k.n_terms; j += A1_THREADS / 32)
-        out[(long long)j * k.n + ge] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane,
-                                                    io.projected_gravity + (long long)ge * 3);
+        out[(long long)j * k.n + ge] = a1_eval_term(k.terms[j], k.rp[j][0], k.rp[j][1], k, s, lane, io, ge);
   }
 }
 

@@ -223,13 +223,18 @@ __device__ V3_NOINLINE void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1
 }
 
 // Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
+template <bool HAS_EXTRA>
 __device__ V3_NOINLINE float v3_eval_term(int code, int q, float p0, float p1, const A1K& k, const V3In& in, int e,
-                                          const float* pg) {
+                                          const ShifuA1StepIO& io, long long ge) {
   const float* cmd = in.cla[0][e];
   const float* lin = in.cla[1][e];
   const float* ang = in.cla[2][e];
-  if (code >= SHIFU_REW_LIN_VEL_Z)       // legged_gym-style terms (rare: pg comes straight from global memory)
-    return a1_extra_term(code, p0, p1, lin, ang, pg, in.dof[e], in.hist[e], in.act[e], in.root[e][2]);
+  if (HAS_EXTRA && code >= SHIFU_REW_LIN_VEL_Z) {   // legged_gym-style terms: pg / air-time state straight from global memory
+    const TermCtx c{cmd, lin, ang, io.projected_gravity + ge * 3, in.dof[e], in.hist[e], in.act[e], in.contact[e],
+                    in.root[e][2], io.swing_time ? io.swing_time + ge * k.n_feet : nullptr,
+                    io.last_contacts ? io.last_contacts + ge * k.n_feet : nullptr};
+    return a1_extra_term(code, p0, p1, k, c);
+  }
   switch (code) {
     case SHIFU_REW_TRACKING_LIN_VEL: {
       const float dx = sub_rn(cmd[0], lin[0]), dy = sub_rn(cmd[1], lin[1]);
@@ -279,7 +284,9 @@ __device__ V3_NOINLINE float v3_eval_term(int code, int q, float p0, float p1, c
 
 // Processes tiles [0, num_tiles) of 32 envs each (the ragged tail, if any, is a separate launch of
 // the barrier-phased kernel).  Requires root_stride == 1 and 16-byte aligned tensors.
-template <bool EXACT_DIV, bool HAS_MROW>
+// HAS_EXTRA: the term list holds a code >= SHIFU_REW_LIN_VEL_Z.  The reference's own six terms run the
+// instantiation without that code (its presence alone cost the B group 5-10 % of the kernel).
+template <bool EXACT_DIV, bool HAS_MROW, bool HAS_EXTRA>
 __global__ void __launch_bounds__(V3_THREADS, V3_CTAS_PER_SM)
 a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant__ ShifuA1StepIO io, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -383,8 +390,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #ifdef V3_WI_NOB1
         s.rterm[j & 1][q][lane] = 0.0f;
 #else
-        s.rterm[j & 1][q][lane] = v3_eval_term(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane,
-                                               io.projected_gravity + ge * 3);
+        s.rterm[j & 1][q][lane] = v3_eval_term<HAS_EXTRA>(k.terms[q], q, k.rp[q][0], k.rp[q][1], k, in, lane, io, ge);
 #endif
       }
       V3_TICK(warp == 0 ? 2 : 6);

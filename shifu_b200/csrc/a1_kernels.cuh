@@ -45,6 +45,11 @@ struct A1K {
   int rp_pow2[SHIFU_MAX_REWARD_TERMS];
   // largest s with sqrt_rn(s) <= threshold: "norm > thr" == "sum of squares > thr_sq" exactly
   float rp_thr_sq[SHIFU_MAX_REWARD_TERMS];
+  // constants of the row-N1 terms (dof-limit, feet-air-time)
+  float dof_lo[A1_DOF], dof_hi[A1_DOF];
+  int n_feet, feet[4];
+  float feet_thr, air_cmd_min, air_dt;
+  int air_reset;
   // term lists of the two B warps of the pipelined kernel (host-side cost balance)
   int term_count[2], term_list[2][SHIFU_MAX_REWARD_TERMS];
   float contact_thr_sq;
@@ -332,6 +337,12 @@ __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& 
   // HistoryRecorder.reset_idx, train.py:16-17
 #pragma unroll
   for (int j = 0; j < A1_DOF * A1_HIST; ++j) hist_row[j] = 0.0f;
+  if (k.air_reset && io.swing_time != nullptr) {                        // legged_gym reset_idx: feet_air_time[env_ids] = 0
+    for (int f = 0; f < k.n_feet; ++f) {
+      io.swing_time[(long long)ge * k.n_feet + f] = 0.0f;
+      io.last_contacts[(long long)ge * k.n_feet + f] = 0;
+    }
+  }
   // sample_command, a1_conditional.py:194-200
   const U4 uc = draw(k.seed, gid, step, STREAM_CMD);
   cmd[0] = add_rn(mul_rn(k.cmd_span[0], u01(uc.x)), k.cmd_low[0]);

@@ -69,6 +69,16 @@ struct ShifuCtx {
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// the pipelined kernel's instantiations, index = 4*EXACT_DIV + 2*HAS_MROW + HAS_EXTRA
+static const void* const* a1_tma_variants() {
+  static const void* const table[8] = {
+      (const void*)a1_post_physics_tma_kernel<false, false, false>, (const void*)a1_post_physics_tma_kernel<false, false, true>,
+      (const void*)a1_post_physics_tma_kernel<false, true, false>,  (const void*)a1_post_physics_tma_kernel<false, true, true>,
+      (const void*)a1_post_physics_tma_kernel<true, false, false>,  (const void*)a1_post_physics_tma_kernel<true, false, true>,
+      (const void*)a1_post_physics_tma_kernel<true, true, false>,   (const void*)a1_post_physics_tma_kernel<true, true, true>};
+  return table;
+}
+
 extern "C" const char* shifu_last_error(void) { return g_err; }
 extern "C" int shifu_abi_version(void) { return SHIFU_ABI_VERSION; }
 
@@ -161,7 +171,16 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   k.contact_thr_sq = sqrt_threshold(d.contact_term_force);
   // Split of the term list over the two B warps of the pipelined kernel: longest-processing-time
   // greedy on rough per-term instruction counts; warp 0 also carries the yaw normalisation (~60).
-  static const int term_cost[SHIFU_REW_COUNT] = {30, 25, 12, 135, 70, 40, 20, 20, 8, 10, 10, 40, 60, 8};
+  for (int i = 0; i < A1_DOF; ++i) { k.dof_lo[i] = d.dof_pos_limit_low[i]; k.dof_hi[i] = d.dof_pos_limit_high[i]; }
+  if (d.num_feet < 0 || d.num_feet > 4) return fail(SHIFU_E_RANGE, "num_feet=%d out of range", d.num_feet);
+  k.n_feet = d.num_feet;
+  for (int i = 0; i < 4; ++i) {
+    if (i < d.num_feet && (d.feet_bodies[i] < 0 || d.feet_bodies[i] >= A1_BODIES))
+      return fail(SHIFU_E_RANGE, "feet_bodies[%d]=%d out of range", i, d.feet_bodies[i]);
+    k.feet[i] = d.feet_bodies[i];
+  }
+  k.feet_thr = d.feet_contact_force; k.air_cmd_min = d.air_time_cmd_min; k.air_dt = d.air_time_dt; k.air_reset = d.air_time_reset;
+  static const int term_cost[SHIFU_REW_COUNT] = {30, 25, 12, 135, 70, 40, 20, 20, 8, 10, 10, 40, 60, 8, 70, 90};
   int load[2] = {60, 0}, order[SHIFU_MAX_REWARD_TERMS];
   for (int i = 0; i < k.n_terms; ++i) order[i] = i;
   auto cost_of = [&](int q) { const int c = k.terms[q]; return (c >= 0 && c < SHIFU_REW_COUNT) ? term_cost[c] : 40; };
@@ -265,9 +284,7 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
     c->a1_grid = tiles < cap ? tiles : cap;
     c->a1_occ = occ;
     // pipelined TMA variants: opt in to the large dynamic shared-memory footprint
-    const void* tma_variants[4] = {      // <EXACT_DIV, HAS_MROW>
-        (const void*)a1_post_physics_tma_kernel<false, false>, (const void*)a1_post_physics_tma_kernel<false, true>,
-        (const void*)a1_post_physics_tma_kernel<true, false>, (const void*)a1_post_physics_tma_kernel<true, true>};
+    const void* const* tma_variants = a1_tma_variants();
     // Ask for just enough shared memory for V3_CTAS_PER_SM resident CTAs (+1 KB the runtime reserves
     // per CTA) and leave the rest of the 256 KB array to L1, which serves the scan-table gathers:
     // 164 KB / 92 KB L1 measured 1.7 % faster than the maximum carve-out (228 KB / 28 KB L1).
@@ -280,14 +297,14 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
       if (carve > 100) carve = 100;
     }
     if (getenv("SHIFU_CARVEOUT") != nullptr) carve = atoi(getenv("SHIFU_CARVEOUT"));
-    for (int v = 0; v < 4 && e == cudaSuccess; ++v) {
+    for (int v = 0; v < 8 && e == cudaSuccess; ++v) {
       e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(tma_variants[v], cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
     int tocc = 0;
     if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, a1_post_physics_tma_kernel<false, false>, V3_THREADS,
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tocc, a1_post_physics_tma_kernel<false, false, false>, V3_THREADS,
                                                         sizeof(V3Smem));
     c->tma_occ = tocc;
     const char* kern = getenv("SHIFU_A1_KERNEL");
@@ -454,11 +471,12 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
     const dim3 grid(full_tiles < cap ? full_tiles : cap), block(V3_THREADS);
     const size_t smem = sizeof(V3Smem);
     const bool mrow = io->measured_heights != nullptr;
-    if (!exact && !mrow) a1_post_physics_tma_kernel<false, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    else if (!exact && mrow) a1_post_physics_tma_kernel<false, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    else if (exact && !mrow) a1_post_physics_tma_kernel<true, false><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    else a1_post_physics_tma_kernel<true, true><<<grid, block, smem, S(stream)>>>(c->a1k, *io, full_tiles);
-    CUDA_TRY(cudaGetLastError());
+    bool extra = false;
+    for (int q = 0; q < c->a1k.n_terms; ++q) extra |= c->a1k.terms[q] >= SHIFU_REW_LIN_VEL_Z;
+    int tiles_arg = full_tiles;
+    void* args[3] = {(void*)&c->a1k, const_cast<ShifuA1StepIO*>(io), (void*)&tiles_arg};
+    CUDA_TRY(cudaLaunchKernel(a1_tma_variants()[(exact ? 4 : 0) + (mrow ? 2 : 0) + (extra ? 1 : 0)], grid, block, args, smem,
+                              S(stream)));
   }
   const int done = full_tiles * A1_TILE;
   if (done < n) {
@@ -477,6 +495,8 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
       t.dof_targets += e * A1_DOF; t.rand_force += e * (A1_BODIES * 3);
       t.obs_buf += e * A1_OBS; t.rew_buf += e; t.reset_buf += e; t.time_out_buf += e; t.contact_term_buf += e;
       if (t.measured_heights != nullptr) t.measured_heights += e * A1_POINTS;
+      if (t.swing_time != nullptr) t.swing_time += e * k.n_feet;
+      if (t.last_contacts != nullptr) t.last_contacts += e * k.n_feet;
     }
     const int tiles = (k.n + A1_TILE - 1) / A1_TILE;
     const int cap = c->sm_count * (c->a1_occ > 0 ? c->a1_occ : 1);

@@ -62,6 +62,30 @@ def _require(fn, what: str, names: Iterable[str] = (), numbers: Iterable[float] 
             raise NotFusable(f"{what}: literal {v} not found (found {sorted(nums)})")
 
 
+_AIR_STATE = {"swing_time", "feet_air_time", "last_contacts"}
+
+
+def _require_reset_idx(cls) -> bool:
+    """The class's reset_idx must be the reference's (a1_conditional.py:89-98), possibly under overrides
+    that only call ``super().reset_idx`` and clear the feet-air-time state (legged_gym's reset_idx does;
+    the kernel's reset then clears it too).  Returns whether the state is cleared on reset."""
+    clears = False
+    for klass in cls.__mro__:
+        fn = klass.__dict__.get("reset_idx")
+        if fn is None:
+            continue
+        names = _names(fn)
+        if {"update_terrain_curriculum", "sample_command"} <= names:
+            return clears or bool(names & _AIR_STATE)
+        other = names - _AIR_STATE - {"super", "reset_idx"}
+        if other or not (names & _AIR_STATE):
+            raise NotFusable(f"reset_idx: {klass.__name__}.reset_idx also touches {sorted(other)} — not a hook the "
+                             "fused kernel replaces")
+        clears = True
+    raise NotFusable("reset_idx: does not reference ['sample_command', 'update_terrain_curriculum'] — not the hook "
+                     "the fused kernel replaces")
+
+
 def _overridden(obj, name: str, base) -> bool:
     return getattr(type(obj), name, None) is not getattr(base, name, None)
 
@@ -109,7 +133,7 @@ def fuse_a1(env, carry_body_frame: bool = True, rng_seed: int = 0x5EED):
         if not hasattr(rb, attr):
             raise NotFusable(f"robot.{attr} is missing")
     # ---- hooks replaced without a numerical check: reference structure by names / literals -----
-    _require(type(env).reset_idx, "reset_idx", ("update_terrain_curriculum", "reset_idx", "sample_command"))
+    air_time_reset = _require_reset_idx(type(env))
     _require(type(env).sample_command, "sample_command",
              ("torch_rand_float", "cmd_lin_vel_x", "cmd_lin_vel_y", "cmd_ang_vel_yaw", "command_buf"))
     _require(type(env).update_terrain_curriculum, "update_terrain_curriculum",
@@ -153,7 +177,9 @@ def fuse_a1(env, carry_body_frame: bool = True, rng_seed: int = 0x5EED):
         base_body=int(env.contact_terminate_indices), leg_bodies=tuple(rb.leg_indices.tolist()),
         force_body=force_body, root_stride=layout[0], root_offset=layout[1],
         action_scale=1.0,                        # a subclass step() has already scaled (a1_conditional.py:122-124)
-        clip_actions=float(env.clip_actions), clip_obs=float(env.clip_obs))
+        clip_actions=float(env.clip_actions), clip_obs=float(env.clip_obs),
+        air_time_reset=air_time_reset,
+        **terms.desc_extras(compiled))
     desc.push_force_max = float(forces[0])
     desc.cmd_low[0], desc.cmd_high[0] = env.cmd_lin_vel_x
     desc.cmd_low[1], desc.cmd_high[1] = env.cmd_lin_vel_y
@@ -168,6 +194,9 @@ def fuse_a1(env, carry_body_frame: bool = True, rng_seed: int = 0x5EED):
              torques=rb.torques, base_lin_vel=rb.base_lin_vel, base_ang_vel=rb.base_ang_vel,
              projected_gravity=rb.projected_gravity, ep_len=env.episode_length_buf, rand_force=rb.rand_force_buf,
              dof_targets=rb.dof_targets, terrain_levels=env.terrain_levels)
+    air = terms.air_time_state(env)
+    if air is not None and any(t.code == nv.REW_FEET_AIR_TIME for t in compiled):
+        hp.adopt(swing_time=air[0], last_contacts=air[1])
     # ---- numerical checks ----------------------------------------------------------------------
     terms.verify_a1_terms(env, hp, env.reward_functions, compiled)
     _check_a1_obs_and_termination(env)

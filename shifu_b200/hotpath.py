@@ -25,6 +25,7 @@ A1_TERM_CODES = {
     # legged_gym-style additions; constants come from shifu_b200.terms (fitted from the hook)
     "lin_vel_z": nv.REW_LIN_VEL_Z, "ang_vel_xy": nv.REW_ANG_VEL_XY, "orientation": nv.REW_ORIENTATION,
     "dof_vel": nv.REW_DOF_VEL, "action_rate": nv.REW_ACTION_RATE, "base_height": nv.REW_BASE_HEIGHT,
+    "dof_pos_limits": nv.REW_DOF_POS_LIMITS, "feet_air_time": nv.REW_FEET_AIR_TIME,
 }
 A1_DEFAULT_TERMS = ("tracking_lin_vel", "tracking_ang_vel", "stabilizing_base", "smoothing_action", "leg_collision",
                     "torques_penalize")              # build_reward_functions() of a1_conditional.py:152-160
@@ -69,7 +70,9 @@ def a1_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
             max_episode_length_s=10., default_root=(0, 0, 0.42, 0, 0, 0, 1.), curriculum=True,
             max_terrain_level=10, num_terrain_types=20, env_length=8., base_body=0,
             leg_bodies=(2, 3, 6, 7, 10, 11, 14, 15), force_body=0, root_stride=1, root_offset=0,
-            action_scale=0.5, clip_actions=1., clip_obs=100.) -> nv.A1Desc:
+            action_scale=0.5, clip_actions=1., clip_obs=100.,
+            dof_pos_limits=None, feet_bodies=(4, 8, 12, 16), feet_contact_force=1.0, air_time_cmd_min=0.1,
+            air_time_dt=0.02, air_time_reset=True) -> nv.A1Desc:
     """Defaults = the constants of ``examples/a1_conditional``."""
     d = nv.A1Desc()
     d.abi_version = nv.ABI_VERSION
@@ -102,6 +105,17 @@ def a1_desc(num_envs: int, *, env_offset: int = 0, rng_seed: int = 0x5EED,
     d.curriculum = int(bool(curriculum))
     d.max_terrain_level, d.num_terrain_types = max_terrain_level, num_terrain_types
     d.level_up_distance, d.level_down_factor = env_length / 2, 0.5
+    # constants of the row-N1 terms: dof_pos_limits (per-dof soft limits) and feet_air_time
+    for i in range(12):
+        lo, hi = dof_pos_limits[i] if dof_pos_limits is not None else (-3.0e38, 3.0e38)
+        d.dof_pos_limit_low[i], d.dof_pos_limit_high[i] = lo, hi
+    if len(feet_bodies) > 4:
+        raise ValueError("at most 4 feet")
+    d.num_feet = len(feet_bodies)
+    for i, b in enumerate(feet_bodies):
+        d.feet_bodies[i] = int(b)
+    d.feet_contact_force, d.air_time_cmd_min, d.air_time_dt = feet_contact_force, air_time_cmd_min, air_time_dt
+    d.air_time_reset = int(bool(air_time_reset))
     comp = compile_reward_terms(list(terms), A1_TERM_CODES, {**A1_TERM_PARAMS, **(term_params or {})})
     d.num_reward_terms = len(comp)
     for i, (code, p0, p1) in enumerate(comp):
@@ -374,6 +388,9 @@ class A1HotPath(_StepStats):
         self.reset_ids = torch.zeros(n, device=dev, dtype=torch.long)
         self.n_reset = torch.zeros(1, device=dev, dtype=torch.int32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.long)
+        # feet-air-time state (legged_gym feet_air_time / last_contacts), used by the term of that name only
+        self.swing_time = torch.zeros(n, max(desc.num_feet, 1), **f)
+        self.last_contacts = torch.zeros(n, max(desc.num_feet, 1), device=dev, dtype=torch.bool)
         self.step_counter = 0
         self._init_stats(dev)
         self._graph, self._graph_warm, self._dev_step, self._graph_actions = None, 0, -1, None
@@ -403,6 +420,7 @@ class A1HotPath(_StepStats):
         io.measured_heights = p(self.measured_heights)
         io.step = self.step_counter
         io.step_dev = p(self.step_dev) if use_step_dev else None
+        io.swing_time, io.last_contacts = p(self.swing_time), p(self.last_contacts)
         io.carry_body_frame = int(self.carry_body_frame)
         return io
 
@@ -418,7 +436,7 @@ class A1HotPath(_StepStats):
         self._io = None
 
     _ADOPTABLE = ("actions", "torques", "history", "command", "ep_len", "base_lin_vel", "base_ang_vel",
-                  "projected_gravity", "terrain_levels", "dof_targets", "rand_force")
+                  "projected_gravity", "terrain_levels", "dof_targets", "rand_force", "swing_time", "last_contacts")
 
     def adopt(self, **tensors):
         """Use the caller's existing tensors instead of the ones allocated here (an env built by user

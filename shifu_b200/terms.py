@@ -42,6 +42,7 @@ class CompiledTerm:
     code: int
     p0: float
     p1: float
+    extra: Optional[dict] = None        # descriptor-level constants of the term (a1_desc keyword -> value)
 
 
 def _strip(name: str) -> str:
@@ -59,7 +60,28 @@ A1_NAMES: Dict[str, int] = {
     "torques_penalize": nv.REW_TORQUES, "torques": nv.REW_TORQUES,
     "lin_vel_z": nv.REW_LIN_VEL_Z, "ang_vel_xy": nv.REW_ANG_VEL_XY, "orientation": nv.REW_ORIENTATION,
     "dof_vel": nv.REW_DOF_VEL, "action_rate": nv.REW_ACTION_RATE, "base_height": nv.REW_BASE_HEIGHT,
+    "dof_pos_limits": nv.REW_DOF_POS_LIMITS, "feet_air_time": nv.REW_FEET_AIR_TIME,
 }
+
+
+def air_time_state(env):
+    """(swing_time, last_contacts) of an env that carries the legged_gym feet-air-time state, else None."""
+    swing = getattr(env, "swing_time", None)
+    swing = getattr(env, "feet_air_time", None) if swing is None else swing
+    last = getattr(env, "last_contacts", None)
+    if torch.is_tensor(swing) and torch.is_tensor(last):
+        return swing, last
+    return None
+
+
+def dof_limits(env) -> torch.Tensor:
+    """(num_dof, 2) limits a dof-limit term reads: ``env.dof_pos_limits`` (legged_gym's soft limits) when the
+    env defines it, else the asset limits of the robot (units/robot.py:39-40)."""
+    lim = getattr(env, "dof_pos_limits", None)
+    if torch.is_tensor(lim):
+        return lim
+    rb = env.robot
+    return torch.stack([rb.dof_lower_limits, rb.dof_upper_limits], dim=1)
 
 
 class A1Probe:
@@ -78,6 +100,9 @@ class A1Probe:
         }
         if getattr(isg, "measured_heights", None) is not None:
             self.tensors["heights"] = isg.measured_heights
+        air = air_time_state(env)
+        if air is not None:
+            self.tensors["swing_time"], self.tensors["last_contacts"] = air
         self._saved = None
         self._attrs = ("obs_buf", "reset_buf", "time_out_buf", "contact_terminate_buf", "rew_buf")
 
@@ -106,6 +131,8 @@ class A1Probe:
         for k, t in self.tensors.items():
             if t.dtype.is_floating_point:
                 t.copy_(torch.randn(t.shape, generator=g, device=t.device) * (0.6 if k != "contact" else 0.4))
+            elif t.dtype == torch.bool:
+                t.copy_(torch.rand(t.shape, generator=g, device=t.device) < 0.5)
             else:
                 t.copy_(torch.randint(0, int(self.env.max_episode_length) + 40, t.shape, generator=g, device=t.device))
         q = self.isg.root_state[:, 3:7]
@@ -197,6 +224,50 @@ def fit_a1_term(pr: A1Probe, fn: Callable, code: int) -> Tuple[float, float]:
             else:
                 lo = mid
         return p0, _snap(0.5 * (lo + hi), fn)
+    if code == nv.REW_DOF_POS_LIMITS:
+        lim = dof_limits(env)
+        if tuple(lim.shape) != (rb.num_dof, 2):
+            raise TermMismatch("dof limits are not a (num_dof, 2) tensor")
+        vals = []
+        for over in (1.0, 2.0):                     # dof 0 that far above its upper limit; the rest unchanged
+            pr.zero()
+            t["dof"].view(env.num_envs, -1, 2)[0, 0, 0] = float(lim[0, 1]) + over
+            vals.append(pr.value(fn))
+        return (_snap(vals[1] - vals[0], fn), 0.0,
+                {"dof_pos_limits": [(float(lo), float(hi)) for lo, hi in lim.tolist()]})
+    if code == nv.REW_FEET_AIR_TIME:
+        if "swing_time" not in t:
+            raise TermMismatch("feet_air_time needs env.swing_time (N, feet) and env.last_contacts (N, feet) bool")
+        feet = [int(b) for b in rb.ee_indices.tolist()]
+        if tuple(t["swing_time"].shape) != (env.num_envs, len(feet)) or len(feet) > 4:
+            raise TermMismatch("swing_time is not (num_envs, num_feet<=4)")
+        cf = t["contact"].view(env.num_envs, -1, 3)
+
+        def landing(air, force=100.0, cmd=1.0):     # foot 0 lands after `air` seconds in the air
+            pr.zero()
+            t["command"][0, 0] = cmd
+            t["swing_time"][0, 0] = air
+            cf[0, feet[0], 2] = force
+            return pr.value(fn)
+
+        r1, r2 = landing(1.0), landing(2.0)
+        p0 = r2 - r1
+        if p0 == 0.0:
+            raise TermMismatch("term does not respond to a landing foot")
+        dt = float(t["swing_time"][0, 1]) if len(feet) > 1 else float(pr.isg.dt)   # a foot in the air gained dt
+        p0 = _snap(p0, fn)
+        p1 = _snap(1.0 + dt - r1 / p0, fn)
+
+        def bisect(lo, hi, responds):
+            for _ in range(60):
+                mid = 0.5 * (lo + hi)
+                lo, hi = (lo, mid) if responds(mid) else (mid, hi)
+            return 0.5 * (lo + hi)
+
+        force_thr = _snap(bisect(0.0, 100.0, lambda f: landing(2.0, force=f) != 0.0), fn)
+        cmd_thr = _snap(bisect(0.0, 1.0, lambda c: landing(2.0, cmd=c) != 0.0), fn)
+        return p0, p1, {"feet_bodies": tuple(feet), "feet_contact_force": force_thr, "air_time_cmd_min": cmd_thr,
+                        "air_time_dt": dt}
     raise TermMismatch(f"no fitting rule for term code {code}")
 
 
@@ -213,8 +284,16 @@ def compile_a1_terms(env, functions: Sequence[Callable], names: Optional[Dict[st
             key = _strip(fn.__name__)
             if key not in names:
                 raise KeyError(f"reward term {fn.__name__!r} has no fused implementation; known: {sorted(names)}")
-            p0, p1 = fit_a1_term(pr, fn, names[key])
-            out.append(CompiledTerm(fn.__name__, names[key], float(p0), float(p1)))
+            p0, p1, *extra = fit_a1_term(pr, fn, names[key])
+            out.append(CompiledTerm(fn.__name__, names[key], float(p0), float(p1), extra[0] if extra else None))
+    return out
+
+
+def desc_extras(terms: Sequence[CompiledTerm]) -> dict:
+    """The a1_desc keywords the compiled terms carry (feet, thresholds, dof limits)."""
+    out = {}
+    for term in terms:
+        out.update(term.extra or {})
     return out
 
 
@@ -222,8 +301,18 @@ def verify_a1_terms(env, hot, functions: Sequence[Callable], terms: Sequence[Com
     """Step 3: user hooks (torch) vs the kernel's term library on the same random state."""
     with A1Probe(env) as pr:
         pr.randomize(seed)
+        stateful = [pr.tensors[k] for k in ("swing_time", "last_contacts") if k in pr.tensors]
+        if stateful:
+            pr.tensors["swing_time"].abs_()
+        before = [t.clone() for t in stateful]
         want = torch.stack([fn().to(torch.float) for fn in functions])
+        after_hooks = [t.clone() for t in stateful]
+        for t, b in zip(stateful, before):          # a stateful term advanced its state: rewind for the kernel's turn
+            t.copy_(b)
         got = hot.eval_terms()
+        for t, a, name in zip(stateful, after_hooks, ("swing_time", "last_contacts")):
+            if not torch.allclose(t.to(torch.float), a.to(torch.float), rtol=RTOL, atol=ATOL):
+                raise TermMismatch(f"feet_air_time: {name} after the Python hook and after the fused term differ")
     for i, term in enumerate(terms):
         err = (got[i] - want[i]).abs()
         tol = ATOL + RTOL * want[i].abs()

@@ -224,6 +224,114 @@ def test_reference_a1_with_edited_constant_or_shape():
     assert torch.isfinite(rew).all() and obs.shape == (meta["n"], 259)
 
 
+def _stateful_class(a1):
+    class AirTime(a1.A1Conditional):                  # legged_gym's two remaining terms: dof limits + feet air time
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.swing_time = torch.zeros(self.num_envs, 4, device=self.device)
+            self.last_contacts = torch.zeros(self.num_envs, 4, dtype=torch.bool, device=self.device)
+            lo, hi = self.robot.dof_lower_limits, self.robot.dof_upper_limits
+            mid, half = (lo + hi) / 2, 0.9 * (hi - lo) / 2          # legged_gym soft_dof_pos_limit = 0.9
+            self.dof_pos_limits = torch.stack([mid - half, mid + half], dim=1)
+
+        def reset_idx(self, env_ids):
+            super().reset_idx(env_ids)
+            self.swing_time[env_ids] = 0.
+            self.last_contacts[env_ids] = False
+
+        def build_reward_functions(self):
+            return [self.tracking_lin_vel, self.tracking_ang_vel, self._reward_feet_air_time,
+                    self._reward_dof_pos_limits, self.leg_collision, self.torques_penalize]
+
+        def _reward_dof_pos_limits(self):
+            out_of_limits = -(self.robot.dof_pos - self.dof_pos_limits[:, 0]).clip(max=0.)
+            out_of_limits += (self.robot.dof_pos - self.dof_pos_limits[:, 1]).clip(min=0.)
+            return -10.0 * torch.sum(out_of_limits, dim=1)
+
+        def _reward_feet_air_time(self):
+            contact = self.robot.contact_forces[:, self.robot.ee_indices, 2] > 1.
+            contact_filt = torch.logical_or(contact, self.last_contacts)
+            self.last_contacts[:] = contact
+            first_contact = (self.swing_time > 0.) * contact_filt
+            self.swing_time += self.isg_env.dt
+            rew = torch.sum((self.swing_time - 0.5) * first_contact, dim=1)
+            rew *= torch.norm(self.command_buf[:, :2], dim=1) > 0.1
+            self.swing_time *= ~contact_filt
+            return 1.0 * rew
+
+    return AirTime
+
+
+@needs_examples
+def test_stateful_legged_gym_terms_fused_vs_hooks():
+    """Row N1: feet_air_time (swing_time / last_contacts carried across steps and zeroed by resets) and
+    dof_pos_limits through the term compiler; the fused env and the same class in user-hook mode replay the
+    same steps and must agree on rewards, episode sums and the air-time state at every step."""
+    from shifu_b200.sim import fake_isaacgym
+    from shifu_b200.sim.synthetic import A1Replay
+    a1, _ = _examples()
+    cls = _stateful_class(a1)
+    z, meta = util.load_golden("a1_small")
+    n = meta["n"]
+
+    def make(fuse):
+        fake_isaacgym.reset_gym()
+        cfg = a1.A1EnvConfig()
+        cfg.num_envs, cfg.device, cfg.rng_seed, cfg.carry_body_frame = n, "cuda:0", meta["rng_seed"], False
+        for k, v in meta["terrain"].items():
+            setattr(cfg.terrain, k, v)
+        np.random.seed(0)
+        env = cls(cfg)
+        env.auto_fuse = fuse
+
+        class Replay(A1Replay):
+            def begin_step(self, step):
+                self.snap = util.golden_snap(z, step)
+                self._dof_i = 0
+                self.enabled = True
+                return self.snap.actions
+
+        env.replay = Replay(0, n, lambda: env.isg_env.env_origins)
+        env.isg_env.sim.provider = env.replay
+        return env
+
+    fused, hooks = make(True), make(False)
+    fused.replay.begin_step(0)
+    fused.reset()
+    assert fused.fusion_report == "fused: a1", fused.fusion_report
+    d = fused.hot.desc
+    codes = [int(d.reward_terms[i]) for i in range(d.num_reward_terms)]
+    assert codes == [0, 1, 15, 14, 4, 5]
+    assert (np.float32(d.reward_params[2][0]), np.float32(d.reward_params[2][1])) == (np.float32(1.0), np.float32(0.5))
+    assert np.float32(d.reward_params[3][0]) == np.float32(-10.0)
+    assert (d.num_feet, list(d.feet_bodies)) == (4, [int(b) for b in fused.robot.ee_indices.tolist()])
+    assert (np.float32(d.feet_contact_force), np.float32(d.air_time_cmd_min)) == (np.float32(1.0), np.float32(0.1))
+    assert np.float32(d.air_time_dt) == np.float32(fused.isg_env.dt) and d.air_time_reset == 1
+    assert np.allclose(np.array(d.dof_pos_limit_low), fused.dof_pos_limits[:, 0].cpu().numpy())
+    assert fused.hot.swing_time.data_ptr() == fused.swing_time.data_ptr()
+    with _philox_draws(a1, hooks, meta["rng_seed"]):
+        hooks.replay.begin_step(0)
+        hooks.reset()
+        assert hooks.fusion_report.startswith("not attempted")
+        for env in (fused, hooks):
+            env.episode_length_buf = torch.from_numpy(z["ep_len_init"]).cuda()
+            env.terrain_levels[:] = torch.from_numpy(z["levels_init"]).cuda()
+        fused.hot.sync_level_sum()
+        landed = 0
+        for t in range(1, meta["steps"] + 1):
+            out = []
+            for env in (fused, hooks):
+                actions = env.replay.begin_step(t)
+                obs, _, rew, dones, _ = env.step(actions.cuda())
+                out.append(dict(obs=obs, rew=rew, dones=dones, swing=env.swing_time, last=env.last_contacts,
+                                **{"sum/" + k: v for k, v in env.episode_rewards.items()}))
+            for k in out[0]:
+                a, b = out[0][k].float(), out[1][k].float()
+                assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (t, k, float((a - b).abs().max()))
+            landed += int((out[0]["sum/_reward_feet_air_time"] != 0).sum())
+        assert landed > 0 and float(fused.swing_time.max()) > 0     # the term fired and the state is live
+
+
 @needs_examples
 def test_reference_abb_pushbox_replays_golden():
     from shifu_b200.sim.synthetic import AbbReplay
