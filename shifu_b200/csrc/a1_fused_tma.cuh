@@ -437,7 +437,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       } else {
         if (reset) {                                                       // state part
           cmd[0] = in.cla[0][lane][0]; cmd[1] = in.cla[0][lane][1]; cmd[2] = in.cla[0][lane][2];
-          a1_reset_env<true, 1>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
+          a1_reset_env<true, 1, HAS_EXTRA>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
                                 st_sum, level_delta, in.origin[lane][0], in.origin[lane][1], in.origin[lane][2],
                                 k.curriculum ? in.level[lane] : 0, k.curriculum ? in.ttype[lane] : 0);
           in.cla[0][lane][0] = cmd[0]; in.cla[0][lane][1] = cmd[1]; in.cla[0][lane][2] = cmd[2];

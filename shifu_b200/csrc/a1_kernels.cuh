@@ -268,7 +268,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // PARTS: 1 = state rewrite (curriculum, dof / root rows, push force, history, command), 2 = episode
 // bookkeeping (length, episode sums -> log sums); the pipelined kernel runs the two on different warps.
-template <bool MIRROR, int PARTS = 3>
+template <bool MIRROR, int PARTS = 3, bool AIR = true>
 __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& io, long long step, int ge,
                                              float* root_row, float* dof_row, float* hist_row,
                                              float (&cmd)[3], float (&esum)[SHIFU_MAX_REWARD_TERMS],
@@ -337,7 +337,7 @@ __device__ __forceinline__ void a1_reset_env(const A1K& k, const ShifuA1StepIO& 
   // HistoryRecorder.reset_idx, train.py:16-17
 #pragma unroll
   for (int j = 0; j < A1_DOF * A1_HIST; ++j) hist_row[j] = 0.0f;
-  if (k.air_reset && io.swing_time != nullptr) {                        // legged_gym reset_idx: feet_air_time[env_ids] = 0
+  if (AIR && k.air_reset && io.swing_time != nullptr) {                      // legged_gym reset_idx: feet_air_time[env_ids] = 0
     for (int f = 0; f < k.n_feet; ++f) {
       io.swing_time[(long long)ge * k.n_feet + f] = 0.0f;
       io.last_contacts[(long long)ge * k.n_feet + f] = 0;
