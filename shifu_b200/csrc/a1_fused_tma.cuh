@@ -14,13 +14,13 @@
 //                        warp 1, while warp 0 does the ordered accumulation and the flags), per-step
 //                        log sums — the scalar game logic of ShifuVecEnv.post_step (env.py:93-106);
 //                        reads only the stage, so it issues no global loads of its own
-//   scan group (12 warps; thread = scan point, warp w: points 32*(w%6).., env batches 2*(w/6), +1)
+//   scan group (12 warps; thread = scan point + its mirror point, warp w: point pairs 32*(w%3)..,
+//                        env pairs 4*(w/3) .. +3 in two items of 4 envs)
 //                        first item's index arithmetic + gathers, then the obs head from the
 //                        post-reset rows (a1_conditional.py:131-144), history push (train.py:12-14),
 //                        carried body-frame velocities, then the rest of the 187-point height scan
-//                        (isaac_gym.py:393-433) in batches of 8 envs with packed fp32x2 arithmetic,
-//                        streamed to HBM with st.global.cs (-DV3_OBS_TMA: staged in shared memory
-//                        and written as 8-row bulk copies instead; measured 1 % slower)
+//                        (isaac_gym.py:393-433) with packed fp32x2 arithmetic (two envs per
+//                        instruction, one yaw rotation per point pair), streamed with st.global.cs
 //
 // mbarriers hand a stage round DMA -> B -> scan -> DMA; every thread of the producing group
 // arrives itself, so fast warps never wait for slow siblings.  The per-env scalars the scan needs
@@ -28,6 +28,9 @@
 // (V3_SCAN_WARPS=6 / V3_CTAS_CFG=3 / V3_STAGES_CFG=2 rebuilds round 1's 3-CTA shape.)
 #pragma once
 #include "a1_fused.cuh"
+#ifndef V3_MIRROR
+#define V3_MIRROR 1
+#endif
 #include "f32x2.cuh"
 #include "tma_pipe.cuh"
 
@@ -78,9 +81,6 @@ constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;
 constexpr int V3_SCAN_BASE = V3_B_THREADS;
 constexpr int V3_DMA_BASE = V3_B_THREADS + V3_C_THREADS;
 static_assert(V3_SCAN_WARPS == 6 || V3_SCAN_WARPS == 12, "scan group: 6 or 12 warps");
-#if defined(V3_OBS_TMA) && V3_SCAN_WARPS != 12
-#error "V3_OBS_TMA is written for the 12-warp scan group (two half-groups of 6 warps)"
-#endif
 constexpr uint32_t V3_OBS_CHUNK_BYTES = 8 * A1_OBS * 4;      // 8288 = 16 * 518
 
 struct alignas(128) V3In {            // one tile of simulator/env rows, each member 16-B aligned
@@ -115,12 +115,6 @@ struct alignas(128) V3Smem {
   // accumulates this tile's
   float rterm[2][SHIFU_MAX_REWARD_TERMS][A1_TILE];
   uint64_t full_in[V3_STAGES], e_done[V3_STAGES], b_done[V3_STAGES], h_done[V3_STAGES];
-#ifdef V3_OBS_TMA
-  // obs rows of the tile, staged as in global memory (row pitch 259 floats): [half-group][item][8 envs]
-  // — a chunk of 8 consecutive envs is one contiguous, 16-byte aligned 8288-byte span on both sides,
-  // written back with ONE bulk copy instead of 8 x 259 scattered 4-byte stores
-  alignas(16) float obs[2][2][8 * A1_OBS];
-#endif
 #ifdef V3_PROFILE
   long long t_issue[V3_STAGES];
 #endif
@@ -461,10 +455,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
   {
     const int p = t - V3_SCAN_BASE;                          // index in the scan group
     const int sw = p >> 5, lane = p & 31;
-#ifdef V3_OBS_TMA
-    constexpr int V3_HALF_THREADS = V3_C_THREADS / 2;         // a half-group = 6 warps = the 16 envs of two items
-    const int hg = p / V3_HALF_THREADS, hl = p % V3_HALF_THREADS;
-#endif
     const float hclip = fminf(k.h_clip, k.clip_obs);         // clip(clip(v,+-a),+-b) == clip(v,+-min(a,b))
     const unsigned max_px = (unsigned)(k.trows - 1), max_py = (unsigned)(k.tcols - 1);
     // banded index: (px>>3)*8*W + py*8 + (px&7)  ==  (px & ~7)*(W-1) + px + 8*py    (3 integer ops)
@@ -494,10 +484,18 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
 #ifndef V3_F2I_CVT
     const f2_t DENORM = pk(__int_as_float(1), __int_as_float(1));     // 2^-149
 #endif
-    // Work items of a tile: (group of 32 scan points, batch of 8 envs).  6 scan warps: warp w owns
-    // point group w for the four env batches.  12 scan warps: warp w owns point group w % 6 for env
-    // batches 2*(w/6) and 2*(w/6)+1.
+    // Work items of a tile.  The measured-point grid is symmetric about the base (point 186 - pt is
+    // -point pt) and round-to-nearest is sign-symmetric, so the yaw rotation of the mirror point is
+    // EXACTLY the negated rotation of the point: a lane owns a point AND its mirror and rotates once.
+    // Item = (group of 32 point pairs [3 groups cover the 94 pairs], batch of 4 envs): warp w owns pair
+    // group w % 3 for the env pairs 2*(V3_ITEMS*(w/3) + it), +1.   (-DV3_MIRROR=0: round 2a's layout,
+    // item = (group of 32 points [6 groups], batch of 8 envs).)
+#if V3_MIRROR
+    static_assert(V3_SCAN_WARPS % 3 == 0 && 8 % (V3_SCAN_WARPS / 3) == 0, "scan warps: 3 pair groups x rows");
+    constexpr int V3_ITEMS = 8 / (V3_SCAN_WARPS / 3);
+#else
     constexpr int V3_ITEMS = (V3_SCAN_WARPS == 12) ? 2 : 4;
+#endif
     V3_T0(p == 0);
     for (int j = 0; j < my_tiles; ++j) {
       const int b = j % V3_STAGES;
@@ -510,23 +508,65 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         // item -> (scan point of this lane, first env pair of the batch)
         struct Item { float bx, by; int q0, pt, it; bool live; };
         auto item = [&](int it) {
+          Item r;
+#if V3_MIRROR
+          const int raw = 32 * (sw % 3) + lane;
+          r.live = raw <= A1_POINTS / 2;                      // pairs 0..93; 93 is the centre, its own mirror
+          r.pt = r.live ? raw : A1_POINTS / 2;                // idle lanes shadow the centre, stores masked
+          r.q0 = 2 * (V3_ITEMS * (sw / 3) + it);
+#else
           int g, qb;
           if (V3_SCAN_WARPS == 12) { g = sw % 6; qb = 2 * (sw / 6) + it; }
           else { g = sw; qb = it; }
-          Item r;
           const int raw = 32 * g + lane;
           r.live = raw < A1_POINTS;
           r.pt = r.live ? raw : A1_POINTS - 1;                // idle lanes shadow the last point, stores masked
-          r.bx = k.px[r.pt % A1_NX]; r.by = k.py[r.pt / A1_NX];
           r.q0 = 4 * qb;
+#endif
+          r.bx = k.px[r.pt % A1_NX]; r.by = k.py[r.pt / A1_NX];
           r.it = it;
           return r;
+        };
+        // Index arithmetic of one item in packed fp32x2 (two envs per instruction).
+        // cell index of the packed pair of positions (ax, ay) [already + base xy + border]: the constant
+        // division, .long() + clip and the banded table offset (isaac_gym.py:416-425)
+        auto cell_pair = [&](f2_t ax, f2_t ay, unsigned& i0, unsigned& i1) {
+          unsigned px0, px1, py0, py1;
+          if (EXACT_DIV) {
+            float a0, a1, b0, b1;
+            upk(ax, a0, a1); upk(ay, b0, b1);
+            // .long() + clip (isaac_gym.py:421-425): float->uint truncates and saturates at 0
+            px0 = min(__float2uint_rz(div_rn(a0, k.hdiv.d)), max_px);
+            px1 = min(__float2uint_rz(div_rn(a1, k.hdiv.d)), max_px);
+            py0 = min(__float2uint_rz(div_rn(b0, k.hdiv.d)), max_py);
+            py1 = min(__float2uint_rz(div_rn(b1, k.hdiv.d)), max_py);
+          } else {                         // q0 = x*r; e = fma(-d, q0, x); q = fma(e, r, q0)
+            const f2_t qx = MUL2(ax, RCP), qy = MUL2(ay, RCP);
+            const f2_t fx = fma2(fma2(NEGD, qx, ax), RCP, qx), fy = fma2(fma2(NEGD, qy, ay), RCP, qy);
+#ifndef V3_F2I_CVT
+            // .long() + clip without the conversion unit: RZ(f * 2^-149) is the denormal whose bit
+            // pattern IS trunc(f) for 0 <= f < 2^23 (negative f -> sign bit -> relu -> 0, larger f
+            // -> a normal number >= 2^23 -> upper clip); one packed multiply per env pair
+            int ix0, ix1, iy0, iy1;
+            upk_i(mulrz2(fx, DENORM), ix0, ix1);
+            upk_i(mulrz2(fy, DENORM), iy0, iy1);
+            px0 = (unsigned)__vimin_s32_relu(ix0, (int)max_px); px1 = (unsigned)__vimin_s32_relu(ix1, (int)max_px);
+            py0 = (unsigned)__vimin_s32_relu(iy0, (int)max_py); py1 = (unsigned)__vimin_s32_relu(iy1, (int)max_py);
+#else
+            float fx0, fx1, fy0, fy1;
+            upk(fx, fx0, fx1); upk(fy, fy0, fy1);
+            px0 = min(__float2uint_rz(fx0), max_px); px1 = min(__float2uint_rz(fx1), max_px);
+            py0 = min(__float2uint_rz(fy0), max_py); py1 = min(__float2uint_rz(fy1), max_py);
+#endif
+          }
+          i0 = ((px0 & ~7u) * c1 + px0) + (py0 << 3);
+          i1 = ((px1 & ~7u) * c1 + px1) + (py1 << 3);
         };
         // Index arithmetic of one item in packed fp32x2 (two envs per instruction).
         auto index_batch = [&](const Item& w, unsigned (&idx)[8]) {
           const f2_t BX = pk(w.bx, w.bx), BY = pk(w.by, w.by), NBY = pk(-w.by, -w.by);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < (V3_MIRROR ? 2 : 4); ++u) {
             const float4 a = s.sA[rb][w.q0 + u], bq = s.sB[rb][w.q0 + u];
             const float2 cq = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u]);
             const f2_t Z2 = pk(a.x, a.y), Z = pk(a.z, a.w), W = pk(bq.x, bq.y), X = pk(bq.z, bq.w);
@@ -540,38 +580,14 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             const f2_t tx = MUL2(Z2, NBY), ty = MUL2(Z2, BX);
             const f2_t rx = SUB2(ADD2(BX, fma2(W, tx, NZ)), fma2(Z, ty, NZ));
             const f2_t ry = ADD2(ADD2(BY, fma2(W, ty, NZ)), fma2(Z, tx, NZ));
-            // + base xy, + border, / horizontal_scale (isaac_gym.py:416-421)
-            const f2_t ax = ADD2(ADD2(rx, X), BORDER), ay = ADD2(ADD2(ry, Y), BORDER);
-            unsigned px0, px1, py0, py1;
-            if (EXACT_DIV) {
-              float a0, a1, b0, b1;
-              upk(ax, a0, a1); upk(ay, b0, b1);
-              // .long() + clip (isaac_gym.py:421-425): float->uint truncates and saturates at 0
-              px0 = min(__float2uint_rz(div_rn(a0, k.hdiv.d)), max_px);
-              px1 = min(__float2uint_rz(div_rn(a1, k.hdiv.d)), max_px);
-              py0 = min(__float2uint_rz(div_rn(b0, k.hdiv.d)), max_py);
-              py1 = min(__float2uint_rz(div_rn(b1, k.hdiv.d)), max_py);
-            } else {                         // q0 = x*r; e = fma(-d, q0, x); q = fma(e, r, q0)
-              const f2_t qx = MUL2(ax, RCP), qy = MUL2(ay, RCP);
-              const f2_t fx = fma2(fma2(NEGD, qx, ax), RCP, qx), fy = fma2(fma2(NEGD, qy, ay), RCP, qy);
-#ifndef V3_F2I_CVT
-              // .long() + clip without the conversion unit: RZ(f * 2^-149) is the denormal whose bit
-              // pattern IS trunc(f) for 0 <= f < 2^23 (negative f -> sign bit -> relu -> 0, larger f
-              // -> a normal number >= 2^23 -> upper clip); one packed multiply per env pair
-              int ix0, ix1, iy0, iy1;
-              upk_i(mulrz2(fx, DENORM), ix0, ix1);
-              upk_i(mulrz2(fy, DENORM), iy0, iy1);
-              px0 = (unsigned)__vimin_s32_relu(ix0, (int)max_px); px1 = (unsigned)__vimin_s32_relu(ix1, (int)max_px);
-              py0 = (unsigned)__vimin_s32_relu(iy0, (int)max_py); py1 = (unsigned)__vimin_s32_relu(iy1, (int)max_py);
+            // + base xy, + border (isaac_gym.py:416-420)
+#if V3_MIRROR
+            cell_pair(ADD2(ADD2(rx, X), BORDER), ADD2(ADD2(ry, Y), BORDER), idx[4 * u], idx[4 * u + 1]);
+            // the mirror point: rotation = (-rx, -ry) exactly, and RN(-r + X) == RN(X - r)
+            cell_pair(ADD2(SUB2(X, rx), BORDER), ADD2(SUB2(Y, ry), BORDER), idx[4 * u + 2], idx[4 * u + 3]);
 #else
-              float fx0, fx1, fy0, fy1;
-              upk(fx, fx0, fx1); upk(fy, fy0, fy1);
-              px0 = min(__float2uint_rz(fx0), max_px); px1 = min(__float2uint_rz(fx1), max_px);
-              py0 = min(__float2uint_rz(fy0), max_py); py1 = min(__float2uint_rz(fy1), max_py);
+            cell_pair(ADD2(ADD2(rx, X), BORDER), ADD2(ADD2(ry, Y), BORDER), idx[2 * u], idx[2 * u + 1]);
 #endif
-            }
-            idx[2 * u] = ((px0 & ~7u) * c1 + px0) + (py0 << 3);
-            idx[2 * u + 1] = ((px1 & ~7u) * c1 + px1) + (py1 << 3);
           }
         };
         auto load_batch = [&](const unsigned (&idx)[8], int (&h)[8]) {
@@ -579,43 +595,39 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
           for (int u = 0; u < 8; ++u) h[u] = v3_gather(table + idx[u]);      // isaac_gym.py:427-431 (folded)
         };
         auto store_batch = [&](const Item& w, const int (&h)[8]) {
-#ifdef V3_OBS_TMA
-          float* ob = &s.obs[hg][w.it][A1_HEAD + w.pt];                       // row u of the chunk: + u * A1_OBS
-#else
           float* ob = io.obs_buf + (e0 + 2 * w.q0) * A1_OBS + A1_HEAD + w.pt;
-#endif
           float* mb = HAS_MROW ? io.measured_heights + (e0 + 2 * w.q0) * A1_POINTS + w.pt : nullptr;
+          // one packed pair of cells -> (z - 0.5) - h*vertical_scale, clipped, to rows r and r+1
+          auto emit = [&](float2 zb, int h0, int h1, float* o, float* m) {
+            const f2_t hg2 = fma2(pk((float)h0, (float)h1), VS, NZ);            // * vertical_scale, :433
+            float v0, v1;
+            upk(SUB2(pk(zb.x, zb.y), hg2), v0, v1);                             // a1_conditional.py:132
+            v3_store(o, clampf(v0, -hclip, hclip));
+            v3_store(o + A1_OBS, clampf(v1, -hclip, hclip));
+            if (HAS_MROW) {
+              float g0, g1;
+              upk(hg2, g0, g1);
+              __stcs(m, g0);
+              __stcs(m + A1_POINTS, g1);
+            }
+          };
           if (w.live) {
+#if V3_MIRROR
+            const int mir = (A1_POINTS - 1) - 2 * w.pt;                         // column of the mirror point
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u].z);
+              emit(zb, h[4 * u], h[4 * u + 1], ob + (2 * u) * A1_OBS, mb + (2 * u) * A1_POINTS);
+              emit(zb, h[4 * u + 2], h[4 * u + 3], ob + (2 * u) * A1_OBS + mir, mb + (2 * u) * A1_POINTS + mir);
+            }
+#else
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u].z);
-              const f2_t hg2 = fma2(pk((float)h[2 * u], (float)h[2 * u + 1]), VS, NZ);   // * vertical_scale, :433
-              float v0, v1;
-              upk(SUB2(pk(zb.x, zb.y), hg2), v0, v1);                           // (z - 0.5) - h, a1_conditional.py:132
-#ifdef V3_OBS_TMA
-              ob[(2 * u) * A1_OBS] = clampf(v0, -hclip, hclip);
-              ob[(2 * u + 1) * A1_OBS] = clampf(v1, -hclip, hclip);
-#else
-              v3_store(ob + (2 * u) * A1_OBS, clampf(v0, -hclip, hclip));
-              v3_store(ob + (2 * u + 1) * A1_OBS, clampf(v1, -hclip, hclip));
-#endif
-              if (HAS_MROW) {
-                float g0, g1;
-                upk(hg2, g0, g1);
-                __stcs(mb + (2 * u) * A1_POINTS, g0);
-                __stcs(mb + (2 * u + 1) * A1_POINTS, g1);
-              }
+              emit(zb, h[2 * u], h[2 * u + 1], ob + (2 * u) * A1_OBS, mb + (2 * u) * A1_POINTS);
             }
-          }
-#ifdef V3_OBS_TMA
-          // chunk complete (head rows + every point group's columns): one bulk store of 8 rows
-          pipe::fence_proxy_async();
-          pipe::named_barrier(2 + hg, V3_HALF_THREADS);
-          if (hl == 0) {
-            pipe::bulk_store(io.obs_buf + (e0 + 2 * w.q0) * A1_OBS, &s.obs[hg][w.it][0], V3_OBS_CHUNK_BYTES);
-            pipe::bulk_commit();
-          }
 #endif
+          }
         };
         // Rolled software pipeline (the body stays small enough for the instruction cache shared with
         // the other warp roles): the gathers of item i are issued at the END of a trip and consumed
@@ -633,24 +645,13 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         V3_TICK(20);
         V3_WAIT(V3_POLL_SCAN, &s.b_done[b], par);
         V3_TICK(8);
-#ifdef V3_OBS_TMA
-        // the bulk stores of the previous tile must have finished READING the obs buffers before the
-        // head rows of this tile go in (the issuing thread waits, the half-group barrier publishes it)
-        if (hl == 0) pipe::bulk_wait_read_all();
-        pipe::named_barrier(2 + hg, V3_HALF_THREADS);
-#endif
         {
           V3In& in = s.in[b];
           const float c = k.clip_obs;
           for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
             const int e = i / A1_DOF, d = i - e * A1_DOF;
-#ifdef V3_OBS_TMA
-            float* hrow = &s.obs[e >> 4][(e >> 3) & 1][(e & 7) * A1_OBS];
-#define V3_HEAD_ST(ptr, v) (*(ptr) = (v))
-#else
             float* hrow = io.obs_buf + (e0 + e) * A1_OBS;
 #define V3_HEAD_ST(ptr, v) __stcs(ptr, v)
-#endif
             const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
             const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
                         a2 = in.hist[e][d * A1_HIST + 2];
@@ -669,11 +670,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             const int e = i / 12, q = i - e * 12;
             const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
 #ifndef V3_WI_NOHEAD
-#ifdef V3_OBS_TMA
-            s.obs[e >> 4][(e >> 3) & 1][(e & 7) * A1_OBS + q] = clampf(v, -c, c);
-#else
             __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
-#endif
 #endif
           }
           // carried body-frame velocities for the next control step (robot.py:222-229, D7): one
@@ -714,9 +711,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       V3_TICK(17);
       V3_COUNT(18);
     }
-#ifdef V3_OBS_TMA
-    if (hl == 0) pipe::bulk_wait_all();                         // obs rows written before the CTA exits
-#endif
   }
 }
 
