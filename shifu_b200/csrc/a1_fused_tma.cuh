@@ -1,42 +1,44 @@
-// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs (2 per SM, 480 threads)
-// with three warp roles that never meet at a CTA-wide barrier —
+// K-main, pipelined form (the default for full 32-env tiles): persistent CTAs (2 per SM, 512 threads =
+// the whole register file at 64 registers) with three warp roles that never meet at a CTA-wide barrier —
 //
 //   DMA warp (1 lane)    bulk-TMA loads (cp.async.bulk -> mbarrier, SASS UBLKCP) of everything the
 //                        tile reads — the root / dof / contact / history / torque / action rows
 //                        and the per-env scalars (ep_len, command, carried velocities, episode
-//                        sums, env origin, terrain level / type) — into a ring of three
-//                        shared-memory stages, refilled as soon as the tile's head phase is over;
-//                        bulk-TMA store of the pushed history tile
-//   B group (2 warps; lane = env)
-//                        yaw normalisation for the scan (first: the scan group starts on e_done),
-//                        the reward-term list (split over both warps by a host-side cost balance) +
-//                        episode sums, termination, reset (curriculum, Philox draws, state rewrite —
-//                        warp 1, while warp 0 does the ordered accumulation and the flags), per-step
-//                        log sums — the scalar game logic of ShifuVecEnv.post_step (env.py:93-106);
-//                        reads only the stage, so it issues no global loads of its own
+//                        sums) — into a ring of three shared-memory stages, refilled as soon as the
+//                        tile's head phase is over; bulk-TMA stores of the pushed history tile and of
+//                        the carried body-frame rows
+//   B group (3 warps; lane = env)
+//                        yaw normalisation for the scan (warp 0, first: the scan group starts on
+//                        e_done), the reward-term list (split over the three warps by a host-side cost
+//                        balance; warp 2 does nothing else and runs ahead into the next tile's terms)
+//                        + episode sums, termination, reset (curriculum, Philox draws, state rewrite
+//                        and the carried body-frame velocities of the post-reset pose — warp 1,
+//                        while warp 0 does the ordered accumulation and the flags), per-step log
+//                        sums — the scalar game logic of ShifuVecEnv.post_step (env.py:93-106);
+//                        reads only the stage (plus env origin / terrain level / type of the ~1 % of
+//                        envs that reset)
 //   scan group (12 warps; thread = scan point + its mirror point, warp w: point pairs 32*(w%3)..,
 //                        env pairs 4*(w/3) .. +3 in two items of 4 envs)
 //                        first item's index arithmetic + gathers, then the obs head from the
 //                        post-reset rows (a1_conditional.py:131-144), history push (train.py:12-14),
-//                        carried body-frame velocities, then the rest of the 187-point height scan
-//                        (isaac_gym.py:393-433) with packed fp32x2 arithmetic (two envs per
-//                        instruction, one yaw rotation per point pair), streamed with st.global.cs
+//                        then the rest of the 187-point height scan (isaac_gym.py:393-433) with
+//                        packed fp32x2 arithmetic (two envs per instruction, one yaw rotation per
+//                        point pair), streamed with st.global.cs
 //
 // mbarriers hand a stage round DMA -> B -> scan -> DMA; every thread of the producing group
 // arrives itself, so fast warps never wait for slow siblings.  The per-env scalars the scan needs
 // travel through a 4-deep ring, which lets the B group run ahead of the scan group.
-// (V3_SCAN_WARPS=6 / V3_CTAS_CFG=3 / V3_STAGES_CFG=2 rebuilds round 1's 3-CTA shape.)
 #pragma once
 #include "a1_fused.cuh"
-#ifndef V3_MIRROR
-#define V3_MIRROR 1
-#endif
 #include "f32x2.cuh"
 #include "tma_pipe.cuh"
 
 namespace shifu {
 
 // B groups of 2 warps each: group g owns the tiles j = g, g + V3_B_GROUPS, ... (dev knob; 1 is fastest)
+#ifndef V3_BG_WARPS_CFG
+#define V3_BG_WARPS_CFG 3
+#endif
 #ifndef V3_B_GROUPS_CFG
 #define V3_B_GROUPS_CFG 1
 #endif
@@ -75,7 +77,10 @@ constexpr int V3_STAGES = V3_STAGES_CFG;          // input stages per CTA (the s
 constexpr int V3_B_GROUPS = V3_B_GROUPS_CFG;
 static_assert(V3_B_GROUPS == 1, "one B group per CTA (the stage ring assumes it)");   // B groups of 2 warps; group g owns tiles j = g, g + V3_B_GROUPS, ...
 constexpr int V3_CTAS_PER_SM = V3_CTAS_CFG;
-constexpr int V3_BG_THREADS = 64, V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 32 * V3_SCAN_WARPS;
+constexpr int V3_BG_WARPS = V3_BG_WARPS_CFG;            // warps 0, 1: terms + B2; further warps: terms only
+static_assert(V3_BG_WARPS >= 2 && V3_BG_WARPS <= A1K_TERM_WARPS, "B group: 2..A1K_TERM_WARPS warps");
+constexpr int V3_BG_THREADS = 32 * V3_BG_WARPS, V3_B2_THREADS = 64;
+constexpr int V3_B_THREADS = V3_B_GROUPS * V3_BG_THREADS, V3_C_THREADS = 32 * V3_SCAN_WARPS;
 constexpr int V3_DMA_THREADS = 32;
 constexpr int V3_THREADS = V3_B_THREADS + V3_C_THREADS + V3_DMA_THREADS;
 constexpr int V3_SCAN_BASE = V3_B_THREADS;
@@ -94,12 +99,12 @@ struct alignas(128) V3In {            // one tile of simulator/env rows, each me
   long long ep_len[A1_TILE];          //   256 B
   float cla[3][A1_TILE][3];           //  1152 B  command (rewritten on reset), base lin vel, base ang vel
   float esum[SHIFU_MAX_REWARD_TERMS][A1_TILE];   // 1024 B  (the first n_terms rows are loaded)
-  float origin[A1_TILE][3];           //   384 B  env_origins           } read by the reset path
-  long long level[A1_TILE];           //   256 B  terrain_levels        } (curriculum only)
-  long long ttype[A1_TILE];           //   256 B  terrain_types         }
+  // output rows: carried body-frame velocities / projected gravity of the POST-reset pose, written by
+  // the B group and bulk-stored by the DMA lane together with the pushed history
+  float cout[3][A1_TILE][3];          //  1152 B
 };
 static_assert(V3_STAGES >= 2 && V3_STAGES <= 4, "ring depth");
-static_assert(sizeof(V3In) == 22272 && offsetof(V3In, ep_len) == 18944, "tile layout");
+static_assert(sizeof(V3In) == 22528 && offsetof(V3In, ep_len) == 18944 && offsetof(V3In, cout) % 16 == 0, "tile layout");
 
 struct alignas(128) V3Smem {
   V3In in[V3_STAGES];
@@ -195,8 +200,7 @@ __device__ __forceinline__ void v3_issue_hist_load(V3In& in, const ShifuA1StepIO
 #endif
 __device__ V3_NOINLINE void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1StepIO& io, long long e0,
                                                uint64_t* bar, bool with_hist) {
-  const uint32_t scalars = sizeof(in.ep_len) + sizeof(in.cla) + k.n_terms * sizeof(in.esum[0]) + sizeof(in.origin) +
-                           (k.curriculum ? sizeof(in.level) + sizeof(in.ttype) : 0);
+  const uint32_t scalars = sizeof(in.ep_len) + sizeof(in.cla) + k.n_terms * sizeof(in.esum[0]);
   pipe::mbar_arrive_expect_tx(bar, V3_ROW_BYTES + scalars);
   pipe::bulk_load(in.root, io.root_state + e0 * 13, sizeof(in.root), bar);
   pipe::bulk_load(in.dof, io.dof_state + e0 * (A1_DOF * 2), sizeof(in.dof), bar);
@@ -209,11 +213,6 @@ __device__ V3_NOINLINE void v3_issue_loads(V3In& in, const A1K& k, const ShifuA1
   pipe::bulk_load(in.cla[1], io.base_lin_vel + e0 * 3, sizeof(in.cla[1]), bar);
   pipe::bulk_load(in.cla[2], io.base_ang_vel + e0 * 3, sizeof(in.cla[2]), bar);
   for (int q = 0; q < k.n_terms; ++q) pipe::bulk_load(in.esum[q], io.ep_sums[q] + e0, sizeof(in.esum[q]), bar);
-  pipe::bulk_load(in.origin, io.env_origins + e0 * 3, sizeof(in.origin), bar);
-  if (k.curriculum) {
-    pipe::bulk_load(in.level, io.terrain_levels + e0, sizeof(in.level), bar);
-    pipe::bulk_load(in.ttype, io.terrain_types + e0, sizeof(in.ttype), bar);
-  }
 }
 
 // Reward term for env e reading the tile rows of `in` (same arithmetic as a1_eval_term).
@@ -258,7 +257,7 @@ __device__ V3_NOINLINE float v3_eval_term(int code, int q, float p0, float p1, c
     }
     case SHIFU_REW_LEG_COLLISION: {
       int cnt = 0;
-      for (int b = 0; b < k.n_leg; ++b) {
+      for (int b = 0; b < k.n_leg; ++b) {   // rolled on purpose: unrolled, the B warps spill (0.4376 vs 0.4289 ms)
         const float* f = &in.contact[e][k.leg[b] * 3];
         // |F| > p1 tested on the sum of squares (threshold pre-squared exactly on the host)
         cnt += (fma_rn(f[2], f[2], fma_rn(f[1], f[1], mul_rn(f[0], f[0]))) > k.rp_thr_sq[q]) ? 1 : 0;
@@ -303,7 +302,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       pipe::mbar_init(&s.full_in[b], 1);
       // every thread of the producing group arrives itself: no group barrier, fast warps move on
       pipe::mbar_init(&s.e_done[b], 32);                     // yaw / xy of the tile's envs are in the ring
-      pipe::mbar_init(&s.b_done[b], V3_BG_THREADS);
+      pipe::mbar_init(&s.b_done[b], V3_B2_THREADS);
       pipe::mbar_init(&s.h_done[b], V3_C_THREADS);
     }
     pipe::fence_barrier_init();
@@ -331,6 +330,11 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       v3_delay(V3_WI_DDELAY);
 #endif
       pipe::bulk_store(io.history + e0 * (A1_DOF * A1_HIST), s.in[b].hist, V3_HIST_BYTES);
+      if (io.carry_body_frame) {                              // robot.py:222-229 for the next control step (D7)
+        pipe::bulk_store(io.base_lin_vel + e0 * 3, s.in[b].cout[0], sizeof(s.in[b].cout[0]));
+        pipe::bulk_store(io.base_ang_vel + e0 * 3, s.in[b].cout[1], sizeof(s.in[b].cout[1]));
+        pipe::bulk_store(io.projected_gravity + e0 * 3, s.in[b].cout[2], sizeof(s.in[b].cout[2]));
+      }
       pipe::bulk_commit();
       V3_STAMP(s.t_issue[b]);
       // every other row of the stage is dead already: refill it while the store still reads hist
@@ -349,7 +353,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     // ---------------- B groups: lane = env ----------------
     const int g = t / V3_BG_THREADS, tg = t % V3_BG_THREADS;   // group g handles tiles j = g, g+2, ...
     const int warp = tg >> 5, lane = tg & 31;
-    V3_T0(g == 0 && lane == 0);
+    V3_T0(g == 0 && lane == 0 && warp < 2);
 
     for (int j = g; j < my_tiles; j += V3_B_GROUPS) {
       const int b = j % V3_STAGES;
@@ -390,6 +394,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
       V3_TICK(warp == 0 ? 2 : 6);
       pipe::named_barrier(1 + g, V3_BG_THREADS);
       V3_TICK(warp == 0 ? 3 : 7);
+      if (warp >= 2) continue;                                 // a terms-only warp: on to the next tile's terms
 
       // ---- B2: both warps decide termination (a1_conditional.py:146-150); warp 0 does the ordered
       //          accumulation, flags and episode bookkeeping, warp 1 the state rewrite of resetting envs
@@ -432,12 +437,26 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         if (reset) {                                                       // state part
           cmd[0] = in.cla[0][lane][0]; cmd[1] = in.cla[0][lane][1]; cmd[2] = in.cla[0][lane][2];
           a1_reset_env<true, 1, HAS_EXTRA>(k, io, step, (int)ge, in.root[lane], in.dof[lane], in.hist[lane], cmd, esum, len,
-                                st_sum, level_delta, in.origin[lane][0], in.origin[lane][1], in.origin[lane][2],
-                                k.curriculum ? in.level[lane] : 0, k.curriculum ? in.ttype[lane] : 0);
+                                st_sum, level_delta, io.env_origins[ge * 3 + 0], io.env_origins[ge * 3 + 1],
+                                io.env_origins[ge * 3 + 2], k.curriculum ? io.terrain_levels[ge] : 0,
+                                k.curriculum ? io.terrain_types[ge] : 0);     // ~1 % of the envs: not worth a stage row
           in.cla[0][lane][0] = cmd[0]; in.cla[0][lane][1] = cmd[1]; in.cla[0][lane][2] = cmd[2];
         }
         reinterpret_cast<float*>(&s.sC[rb][lane >> 1])[2 + (lane & 1)] =
             sub_rn(in.root[lane][2], k.h_off);                              // post-reset base z (D8)
+        if (io.carry_body_frame) {
+          // carried body-frame velocities for the next control step (robot.py:222-229, D7), from the
+          // post-reset root row of this lane's env; the rows leave with the DMA lane's bulk stores
+          const float* r = in.root[lane];
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            float o[3];
+            rotate_inverse(r + 3, v == 2 ? 0.0f : r[7 + 3 * v], v == 2 ? 0.0f : r[8 + 3 * v],
+                           v == 2 ? -1.0f : r[9 + 3 * v], o);
+            in.cout[v][lane][0] = o[0]; in.cout[v][lane][1] = o[1]; in.cout[v][lane][2] = o[2];
+          }
+          pipe::fence_proxy_async();                           // -> visible to the bulk stores
+        }
         a1_log_sums<1>(k, reset, st_sum, level_delta, lane);
       }
 #ifdef V3_WI_BDELAY
@@ -488,14 +507,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
     // -point pt) and round-to-nearest is sign-symmetric, so the yaw rotation of the mirror point is
     // EXACTLY the negated rotation of the point: a lane owns a point AND its mirror and rotates once.
     // Item = (group of 32 point pairs [3 groups cover the 94 pairs], batch of 4 envs): warp w owns pair
-    // group w % 3 for the env pairs 2*(V3_ITEMS*(w/3) + it), +1.   (-DV3_MIRROR=0: round 2a's layout,
-    // item = (group of 32 points [6 groups], batch of 8 envs).)
-#if V3_MIRROR
+    // group w % 3 for the env pairs 2*(V3_ITEMS*(w/3) + it), +1.  (The host routes grids that are not
+    // point-symmetric to the phased kernel.)
     static_assert(V3_SCAN_WARPS % 3 == 0 && 8 % (V3_SCAN_WARPS / 3) == 0, "scan warps: 3 pair groups x rows");
     constexpr int V3_ITEMS = 8 / (V3_SCAN_WARPS / 3);
-#else
-    constexpr int V3_ITEMS = (V3_SCAN_WARPS == 12) ? 2 : 4;
-#endif
     V3_T0(p == 0);
     for (int j = 0; j < my_tiles; ++j) {
       const int b = j % V3_STAGES;
@@ -509,20 +524,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         struct Item { float bx, by; int q0, pt, it; bool live; };
         auto item = [&](int it) {
           Item r;
-#if V3_MIRROR
           const int raw = 32 * (sw % 3) + lane;
           r.live = raw <= A1_POINTS / 2;                      // pairs 0..93; 93 is the centre, its own mirror
           r.pt = r.live ? raw : A1_POINTS / 2;                // idle lanes shadow the centre, stores masked
           r.q0 = 2 * (V3_ITEMS * (sw / 3) + it);
-#else
-          int g, qb;
-          if (V3_SCAN_WARPS == 12) { g = sw % 6; qb = 2 * (sw / 6) + it; }
-          else { g = sw; qb = it; }
-          const int raw = 32 * g + lane;
-          r.live = raw < A1_POINTS;
-          r.pt = r.live ? raw : A1_POINTS - 1;                // idle lanes shadow the last point, stores masked
-          r.q0 = 4 * qb;
-#endif
           r.bx = k.px[r.pt % A1_NX]; r.by = k.py[r.pt / A1_NX];
           r.it = it;
           return r;
@@ -566,7 +571,7 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         auto index_batch = [&](const Item& w, unsigned (&idx)[8]) {
           const f2_t BX = pk(w.bx, w.bx), BY = pk(w.by, w.by), NBY = pk(-w.by, -w.by);
 #pragma unroll
-          for (int u = 0; u < (V3_MIRROR ? 2 : 4); ++u) {
+          for (int u = 0; u < 2; ++u) {
             const float4 a = s.sA[rb][w.q0 + u], bq = s.sB[rb][w.q0 + u];
             const float2 cq = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u]);
             const f2_t Z2 = pk(a.x, a.y), Z = pk(a.z, a.w), W = pk(bq.x, bq.y), X = pk(bq.z, bq.w);
@@ -581,13 +586,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             const f2_t rx = SUB2(ADD2(BX, fma2(W, tx, NZ)), fma2(Z, ty, NZ));
             const f2_t ry = ADD2(ADD2(BY, fma2(W, ty, NZ)), fma2(Z, tx, NZ));
             // + base xy, + border (isaac_gym.py:416-420)
-#if V3_MIRROR
             cell_pair(ADD2(ADD2(rx, X), BORDER), ADD2(ADD2(ry, Y), BORDER), idx[4 * u], idx[4 * u + 1]);
             // the mirror point: rotation = (-rx, -ry) exactly, and RN(-r + X) == RN(X - r)
             cell_pair(ADD2(SUB2(X, rx), BORDER), ADD2(SUB2(Y, ry), BORDER), idx[4 * u + 2], idx[4 * u + 3]);
-#else
-            cell_pair(ADD2(ADD2(rx, X), BORDER), ADD2(ADD2(ry, Y), BORDER), idx[2 * u], idx[2 * u + 1]);
-#endif
           }
         };
         auto load_batch = [&](const unsigned (&idx)[8], int (&h)[8]) {
@@ -612,7 +613,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             }
           };
           if (w.live) {
-#if V3_MIRROR
             const int mir = (A1_POINTS - 1) - 2 * w.pt;                         // column of the mirror point
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -620,13 +620,6 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
               emit(zb, h[4 * u], h[4 * u + 1], ob + (2 * u) * A1_OBS, mb + (2 * u) * A1_POINTS);
               emit(zb, h[4 * u + 2], h[4 * u + 3], ob + (2 * u) * A1_OBS + mir, mb + (2 * u) * A1_POINTS + mir);
             }
-#else
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 zb = *reinterpret_cast<const float2*>(&s.sC[rb][w.q0 + u].z);
-              emit(zb, h[2 * u], h[2 * u + 1], ob + (2 * u) * A1_OBS, mb + (2 * u) * A1_POINTS);
-            }
-#endif
           }
         };
         // Rolled software pipeline (the body stays small enough for the instruction cache shared with
@@ -648,6 +641,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         {
           V3In& in = s.in[b];
           const float c = k.clip_obs;
+#ifdef V3_WI_NOHEADALL
+          if (k.n < 0)
+#endif
           for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
             const int e = i / A1_DOF, d = i - e * A1_DOF;
             float* hrow = io.obs_buf + (e0 + e) * A1_OBS;
@@ -666,6 +662,10 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             in.hist[e][d * A1_HIST + 1] = a0;
             in.hist[e][d * A1_HIST + 0] = in.act[e][d];
           }
+          V3_TICK(21);
+#if defined(V3_WI_NOHEADALL) || defined(V3_WI_NOCLA)
+          if (k.n < 0)
+#endif
           for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
             const int e = i / 12, q = i - e * 12;
             const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
@@ -673,23 +673,9 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
             __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
 #endif
           }
-          // carried body-frame velocities for the next control step (robot.py:222-229, D7): one
-          // rotation per (env, vector) item on half of the scan warps, the halves alternating from tile
-          // to tile so that no warp is permanently the slowest of the group
-          if (io.carry_body_frame) {
-            const int it = p - ((j & 1) ? V3_C_THREADS / 2 : 0);  // item = (vector, env): 3 x 32
-            if (it >= 0 && it < 96) {
-              const int v = it >> 5, e = it & 31;
-              const long long ge = e0 + e;
-              const float* r = in.root[e];
-              float o[3];
-              rotate_inverse(r + 3, v == 2 ? 0.0f : r[7 + 3 * v], v == 2 ? 0.0f : r[8 + 3 * v],
-                             v == 2 ? -1.0f : r[9 + 3 * v], o);
-              float* dst = (v == 0 ? io.base_lin_vel : (v == 1 ? io.base_ang_vel : io.projected_gravity)) + ge * 3;
-              dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
-            }
-          }
+          V3_TICK(22);
         }
+        V3_TICK(23);
         pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
         pipe::mbar_arrive(&s.h_done[b]);
         V3_TICK(9);

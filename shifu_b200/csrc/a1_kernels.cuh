@@ -20,6 +20,8 @@ constexpr int A1_THREADS = 192;   // 6 warps: 187 scan points + 5 idle lanes
 constexpr int TILE_SHIFT = 3;     // scan table stored in bands of 8 map rows: a 128-B line = 8x8 cells
 
 // Kernel-side constants (passed by value as a __grid_constant__ parameter: constant bank).
+constexpr int A1K_TERM_WARPS = 4;     // the pipelined kernel splits the term list over up to this many warps
+
 struct A1K {
   int n;
   long long env_offset;
@@ -51,7 +53,7 @@ struct A1K {
   float feet_thr, air_cmd_min, air_dt;
   int air_reset;
   // term lists of the two B warps of the pipelined kernel (host-side cost balance)
-  int term_count[2], term_list[2][SHIFU_MAX_REWARD_TERMS];
+  int term_count[A1K_TERM_WARPS], term_list[A1K_TERM_WARPS][SHIFU_MAX_REWARD_TERMS];
   float contact_thr_sq;
   // scan table
   const short* table;     // tiled min-of-3 table

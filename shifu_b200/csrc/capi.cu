@@ -65,6 +65,7 @@ struct ShifuCtx {
   int a1_occ = 0;
   int tma_occ = 0;
   bool use_tma = true;
+  bool grid_symmetric = false;     // measured-point grid is point-symmetric (what the pipelined scan assumes)
 };
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -108,6 +109,12 @@ static float sqrt_threshold(float thr) {
   return s;
 }
 
+#ifndef V3_LOAD0
+#define V3_LOAD0 215
+#endif
+#ifndef V3_LOAD1
+#define V3_LOAD1 160
+#endif
 static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   if (d.abi_version != SHIFU_ABI_VERSION) return fail(SHIFU_E_RANGE, "ShifuA1Desc.abi_version %d != %d", d.abi_version, SHIFU_ABI_VERSION);
   if (d.num_envs <= 0) return fail(SHIFU_E_RANGE, "num_envs must be > 0 (got %d)", d.num_envs);
@@ -181,15 +188,21 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   }
   k.feet_thr = d.feet_contact_force; k.air_cmd_min = d.air_time_cmd_min; k.air_dt = d.air_time_dt; k.air_reset = d.air_time_reset;
   static const int term_cost[SHIFU_REW_COUNT] = {30, 25, 12, 135, 70, 40, 20, 20, 8, 10, 10, 40, 60, 8, 70, 90};
-  int load[2] = {60, 0}, order[SHIFU_MAX_REWARD_TERMS];
+  // longest-processing-time split of the term list over the B warps of the pipelined kernel.  Warp 0
+  // starts loaded with the yaw normalisation it does first (~115 on the scale of term_cost, from the
+  // phase timers); with terms-only warps present, warps 0 and 1 also carry their B2 halves (~100
+  // each), which a terms-only warp overlaps with the next tile's terms.
+  int load[A1K_TERM_WARPS] = {0}, order[SHIFU_MAX_REWARD_TERMS];
+  load[0] = V3_BG_WARPS > 2 ? V3_LOAD0 : 60; load[1] = V3_BG_WARPS > 2 ? V3_LOAD1 : 0;
   for (int i = 0; i < k.n_terms; ++i) order[i] = i;
   auto cost_of = [&](int q) { const int c = k.terms[q]; return (c >= 0 && c < SHIFU_REW_COUNT) ? term_cost[c] : 40; };
   for (int i = 0; i < k.n_terms; ++i)
     for (int j = i + 1; j < k.n_terms; ++j)
       if (cost_of(order[j]) > cost_of(order[i])) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-  k.term_count[0] = k.term_count[1] = 0;
+  for (int w = 0; w < A1K_TERM_WARPS; ++w) k.term_count[w] = 0;
   for (int i = 0; i < k.n_terms; ++i) {
-    const int w = load[1] < load[0] ? 1 : 0;
+    int w = 0;
+    for (int v = 1; v < V3_BG_WARPS; ++v) if (load[v] < load[w]) w = v;
     k.term_list[w][k.term_count[w]++] = order[i];
     load[w] += cost_of(order[i]);
   }
@@ -258,7 +271,12 @@ static int ctx_create_impl(int device, const ShifuA1Desc* a1, const ShifuAbbDesc
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   int n = 0;
-  if (a1 != nullptr) { c->is_a1 = true; c->a1 = *a1; c->a1k = a1k; n = a1->num_envs; }
+  if (a1 != nullptr) {
+    c->is_a1 = true; c->a1 = *a1; c->a1k = a1k; n = a1->num_envs;
+    c->grid_symmetric = true;
+    for (int i = 0; i < A1_NX; ++i) c->grid_symmetric &= (a1k.px[i] == -a1k.px[A1_NX - 1 - i]);
+    for (int i = 0; i < A1_NY; ++i) c->grid_symmetric &= (a1k.py[i] == -a1k.py[A1_NY - 1 - i]);
+  }
   else if (abb != nullptr) { c->is_abb = true; c->abb = *abb; c->abbk = abbk; n = abb->num_envs; }
   else n = util_envs;
   cudaError_t e = cudaMalloc(&c->d_stats, sizeof(double) * (SHIFU_NUM_STATS + 1));
@@ -459,11 +477,11 @@ extern "C" int shifu_a1_post_physics(ShifuCtx* c, const ShifuA1StepIO* io, void*
   // (contiguous root rows, 16-byte aligned tensors); the barrier-phased kernel takes the ragged
   // tail (< 32 envs) or everything when bulk copies are not possible.
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool can_tma = c->use_tma && tiled && c->a1k.root_stride == 1 && c->a1k.root_offset == 0 && al16(io->root_state) &&
+  // the pipelined scan rotates once per point pair: it needs the point-symmetric grid (else: phased kernel)
+  const bool can_tma = c->use_tma && tiled && c->grid_symmetric && c->a1k.root_stride == 1 && c->a1k.root_offset == 0 && al16(io->root_state) &&
                        al16(io->dof_state) && al16(io->contact_state) && al16(io->history) && al16(io->torques) &&
                        al16(io->actions) && al16(io->obs_buf) && al16(io->ep_len) && al16(io->command) &&
-                       al16(io->base_lin_vel) && al16(io->base_ang_vel) && al16(io->env_origins) &&
-                       (!c->a1k.curriculum || (al16(io->terrain_levels) && al16(io->terrain_types))) &&
+                       al16(io->base_lin_vel) && al16(io->base_ang_vel) && al16(io->projected_gravity) &&
                        [&] { for (int q = 0; q < c->a1k.n_terms; ++q) if (!al16(io->ep_sums[q])) return false; return true; }();
   const int full_tiles = can_tma ? n / A1_TILE : 0;
   if (full_tiles > 0) {

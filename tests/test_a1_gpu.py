@@ -213,6 +213,28 @@ def test_exact_division_variant_matches_oracle():
         util.compare_a1(util.cuda_a1_outputs(hp), util.oracle_a1_outputs(st), f"hscale0.13/s{t}")
 
 
+def test_asymmetric_point_grid_matches_oracle():
+    """The pipelined kernel rotates once per point PAIR, which needs measured_points symmetric about the
+    base; any other 17x11 grid (here: shifted forward, uneven rows) must be routed to the phased kernel
+    and still match the oracle cell for cell."""
+    from oracle import shifu_oracle as so
+    from shifu_b200.sim.synthetic import a1_snapshot
+    n = 32 * 6 + 3
+    hs, origins, types, env_origins = _terrain(n)
+    px = [round(-0.6 + 0.1 * i, 3) for i in range(17)]            # -0.6 .. 1.0: looks further ahead
+    py = [-0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.25, 0.4, 0.55, 0.7]
+    p, st = util.make_oracle_a1(n, hs, origins, types, env_origins, points_x=px, points_y=py)
+    hp = util.make_cuda_a1(n, hs, origins, types, env_origins, points_x=px, points_y=py)
+    so.a1_reset(p, st, a1_snapshot(6, 0, n, p_base=0.05))
+    hp.reset_idx(None)
+    util.cuda_a1_step(hp, a1_snapshot(6, 0, n, p_base=0.05), torch.zeros(n, 12))
+    for t in range(1, 3):
+        snap = a1_snapshot(6, t, n, p_base=0.05)
+        so.a1_step(p, st, snap.actions, snap)
+        util.cuda_a1_step(hp, snap, snap.actions)
+        util.compare_a1(util.cuda_a1_outputs(hp), util.oracle_a1_outputs(st), f"asym-grid/s{t}")
+
+
 def test_kernel_instantiations_agree(monkeypatch):
     """The pipelined kernel with / without measured_heights and the barrier-phased kernel are the
     same function: bit-identical outputs on the same inputs (the bench runs without

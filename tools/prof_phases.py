@@ -8,7 +8,7 @@ from shifu_b200 import _native as nv
 
 NAMES = {19: "TMA issue->w1 sees full_in", 0: "B.w0 loop top", 1: "B.w0 wait full_in(+s_free)", 2: "B.w0 B1", 3: "B.w0 barrier2", 13: "B.w0 B2",
          4: "B.w1 pre", 5: "B.w1 wait full_in", 6: "B.w1 B1", 7: "B.w1 barrier2", 14: "B.w1 B2(idle)",
-         9: "scan-group head", 10: "DMA wait h_done", 11: "DMA store+reload",
+         9: "scan head: fence + arrive", 21: "scan head: (env,dof) items", 22: "scan head: cla items", 23: "scan head: carry", 10: "DMA wait h_done", 11: "DMA store+reload",
          16: "scan wait e_done", 20: "scan prologue (item 0 index+gather)", 8: "scan wait b_done", 17: "scan work"}
 COUNTS = {15: "B tiles", 12: "head tiles", 18: "scan tiles"}
 
