@@ -639,46 +639,38 @@ a1_post_physics_tma_kernel(const __grid_constant__ A1K k, const __grid_constant_
         V3_WAIT(V3_POLL_SCAN, &s.b_done[b], par);
         V3_TICK(8);
         {
+          // One (env, dof) item and one (env, column) item per thread.  Everything the head reads from the
+          // stage is loaded FIRST and the history is pushed, then the stage is handed back (fence + arrive),
+          // and only then are the 6 observation values clamped and stored: the MEMBAR behind
+          // fence.proxy.async waits for every memory operation the thread has in flight, so with the
+          // global stores issued before it the stage release waited for their acknowledgements.
+          static_assert(A1_TILE * A1_DOF == V3_C_THREADS && A1_TILE * 12 == V3_C_THREADS, "one item per scan thread");
           V3In& in = s.in[b];
           const float c = k.clip_obs;
-#ifdef V3_WI_NOHEADALL
-          if (k.n < 0)
-#endif
-          for (int i = p; i < A1_TILE * A1_DOF; i += V3_C_THREADS) {     // (env, dof) items
-            const int e = i / A1_DOF, d = i - e * A1_DOF;
-            float* hrow = io.obs_buf + (e0 + e) * A1_OBS;
-#define V3_HEAD_ST(ptr, v) __stcs(ptr, v)
-            const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
-            const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
-                        a2 = in.hist[e][d * A1_HIST + 2];
-#ifndef V3_WI_NOHEAD
-            V3_HEAD_ST(hrow + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
-            V3_HEAD_ST(hrow + 24 + d, clampf(qd.y, -c, c));
-            V3_HEAD_ST(hrow + 36 + d, clampf(a0, -c, c));       // HistoryRecorder.flatten: slot-major
-            V3_HEAD_ST(hrow + 48 + d, clampf(a1, -c, c));
-            V3_HEAD_ST(hrow + 60 + d, clampf(a2, -c, c));
-#endif
-            in.hist[e][d * A1_HIST + 2] = a1;            // HistoryRecorder.add
-            in.hist[e][d * A1_HIST + 1] = a0;
-            in.hist[e][d * A1_HIST + 0] = in.act[e][d];
-          }
+          const int e = p / A1_DOF, d = p - e * A1_DOF;                    // e, d serve both items (12 columns each)
+          float* hrow = io.obs_buf + (e0 + e) * A1_OBS;
+          const float2 qd = *reinterpret_cast<const float2*>(&in.dof[e][2 * d]);
+          const float a0 = in.hist[e][d * A1_HIST + 0], a1 = in.hist[e][d * A1_HIST + 1],
+                      a2 = in.hist[e][d * A1_HIST + 2];
+          const float v = (d < 9) ? in.cla[d / 3][e][d % 3] : ((d == 11) ? -1.0f : 0.0f);   // command, velocities, gravity_vec
+          in.hist[e][d * A1_HIST + 2] = a1;              // HistoryRecorder.add (train.py:12-14)
+          in.hist[e][d * A1_HIST + 1] = a0;
+          in.hist[e][d * A1_HIST + 0] = in.act[e][d];
           V3_TICK(21);
-#if defined(V3_WI_NOHEADALL) || defined(V3_WI_NOCLA)
-          if (k.n < 0)
-#endif
-          for (int i = p; i < A1_TILE * 12; i += V3_C_THREADS) {          // command, velocities, gravity_vec
-            const int e = i / 12, q = i - e * 12;
-            const float v = (q < 9) ? in.cla[q / 3][e][q % 3] : ((q == 11) ? -1.0f : 0.0f);
+          pipe::fence_proxy_async();                            // pushed history -> visible to the TMA store
+          pipe::mbar_arrive(&s.h_done[b]);
+          V3_TICK(9);
 #ifndef V3_WI_NOHEAD
-            __stcs(io.obs_buf + (e0 + e) * A1_OBS + q, clampf(v, -c, c));
+#define V3_HEAD_ST(ptr, v) __stcs(ptr, v)
+          V3_HEAD_ST(hrow + d, clampf(v, -c, c));
+          V3_HEAD_ST(hrow + 12 + d, clampf(sub_rn(qd.x, k.q0[d]), -c, c));
+          V3_HEAD_ST(hrow + 24 + d, clampf(qd.y, -c, c));
+          V3_HEAD_ST(hrow + 36 + d, clampf(a0, -c, c));         // HistoryRecorder.flatten: slot-major
+          V3_HEAD_ST(hrow + 48 + d, clampf(a1, -c, c));
+          V3_HEAD_ST(hrow + 60 + d, clampf(a2, -c, c));
 #endif
-          }
           V3_TICK(22);
         }
-        V3_TICK(23);
-        pipe::fence_proxy_async();                              // pushed history -> visible to the TMA store
-        pipe::mbar_arrive(&s.h_done[b]);
-        V3_TICK(9);
 #ifdef V3_WI_SDELAY
         v3_delay(V3_WI_SDELAY);
 #endif
