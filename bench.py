@@ -517,7 +517,7 @@ def run_ours(args):
                            reset_fraction_per_step=reset_frac,
                            launch="one CUDA-graph replay per step (9 kernels)" if graphed else "direct (9 launches/step)",
                            collective="all_reduce(16 x f64) per step on a side stream" if world > 1 else "none"),
-            "roofline": {"bound": "hbm", "kernel": "a1_post_physics_tma_kernel<0,0>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "a1_post_physics_tma_kernel<0,0,0>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_env": B_ALG_POST,
                          "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step,
@@ -553,7 +553,7 @@ def run_ours(args):
         tot2 = time_steps(env2, raw2, args.steps, args.warmup)
         k2 = statistics.mean(time_fused_kernel(env2.hot))
         line["with_measured_heights"] = {
-            "value": n / (tot2 / args.steps * 1e-3), "ms_per_step": tot2 / args.steps, "kernel": "a1_post_physics_tma_kernel<0,1>",
+            "value": n / (tot2 / args.steps * 1e-3), "ms_per_step": tot2 / args.steps, "kernel": "a1_post_physics_tma_kernel<0,1,0>",
             "kernel_ms": k2, "algorithmic_bytes_per_env": B_ALG_POST + 748,
             "frac": (B_ALG_POST + 748) * n / (k2 * 1e-3) / 1e9 / peak,
             "frac_on_1819_bytes": B_ALG_POST * n / (k2 * 1e-3) / 1e9 / peak}
