@@ -69,7 +69,7 @@ enum ShifuRewardTerm {
   SHIFU_REW_BASE_HEIGHT = 13,     /* p0*(z - p1)^2                    square(base_pose[:, 2] - p1) */
   SHIFU_REW_DOF_POS_LIMITS = 14,  /* p0*sum(-(q - lo).clip(max=0) + (q - hi).clip(min=0))   lo/hi = dof_pos_limit_low/high */
   SHIFU_REW_FEET_AIR_TIME = 15,   /* p0*sum((air_time + dt - p1) * first_contact) * [|cmd_xy| > air_time_cmd_min];
-                                     STATEFUL: swing_time / last_contacts (a1_conditional.py:100-103) are
+                                     STATEFUL: swing_time / last_contacts (a1_conditional.py:99-102) are
                                      updated exactly like legged_gym's _reward_feet_air_time */
   SHIFU_REW_COUNT = 16
 };

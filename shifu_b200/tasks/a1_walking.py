@@ -147,6 +147,9 @@ class A1Conditional(ShifuVecEnv):
         self.command_buf = torch.zeros(n, self.num_commands, dtype=torch.float32, device=dev)
         self.contact_terminate_indices = self.isg_env.gym.find_actor_rigid_body_handle(
             self.isg_env.env_handles[0], self.robot.actor_handle, 'base')
+        # a1_conditional.py:99-102 (read by a feet_air_time term, if a subclass lists one)
+        self.swing_time = torch.zeros(n, self.robot.ee_indices.shape[0], dtype=torch.float, device=dev)
+        self.last_contacts = torch.zeros(n, len(self.robot.ee_indices), dtype=torch.bool, device=dev)
         self.contact_terminate_buf = torch.zeros(n, dtype=torch.bool, device=dev)
         self.terrain_levels = torch.zeros(n, dtype=torch.long, device=dev)
         self.hot = None
@@ -188,6 +191,8 @@ class A1Conditional(ShifuVecEnv):
         self.time_out_buf, self.contact_terminate_buf = hp.time_out_buf, hp.contact_terminate_buf
         self.episode_rewards = hp.ep_sums
         self.command_buf, self.terrain_levels = hp.command, hp.terrain_levels
+        if hp.swing_time.shape == self.swing_time.shape:
+            self.swing_time, self.last_contacts = hp.swing_time, hp.last_contacts
         self.actions_recorder.history_buf = hp.history
         rb.torques, rb.dof_targets, rb.rand_force_buf = hp.torques, hp.dof_targets, hp.rand_force
         rb.base_lin_vel, rb.base_ang_vel = hp.base_lin_vel, hp.base_ang_vel
