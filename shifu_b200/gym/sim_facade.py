@@ -239,8 +239,10 @@ class TerrainGymEnv(IsaacGymEnv):
         tc = self.cfg.terrain
         if tc.mesh_type not in ('heightfield', 'trimesh'):
             raise NotImplementedError("cfg.terrain.mesh_type must be one of heightfield or trimesh")
-        # cfg.terrain.generator = "device": the map is rasterised by shifu_terrain_generate (row N3)
-        on_device = getattr(tc, "generator", "host") == "device" and str(self.device).startswith("cuda")
+        # Row N3: on a CUDA device the map is rasterised by shifu_terrain_generate (bit-identical to the
+        # host builder, which remains the path for the closed-source Isaac Gym generators and for
+        # cfg.terrain.generator = "host")
+        on_device = getattr(tc, "generator", "auto") in ("auto", "device") and str(self.device).startswith("cuda")
         self.terrain = Terrain(tc, self.num_envs, device=self.device if on_device else None)
         params = gymapi.HeightFieldParams() if tc.mesh_type == 'heightfield' else gymapi.TriangleMeshParams()
         params.transform.p.x = params.transform.p.y = -tc.border_size

@@ -8,7 +8,7 @@ initialisation; the hot path only consumes the resulting int16 tensor (``shifu_b
 scan reads a banded min-of-3 copy of it).
 
 Two builders: the host one below (numpy, tile by tile, works with whatever ``isaacgym.terrain_utils``
-provides) and — ``Terrain(cfg, n, device="cuda:0")`` or ``cfg.generator = "device"`` — the device
+provides) and — ``Terrain(cfg, n, device="cuda:0")``; the default of ``TerrainGymEnv`` on a CUDA device, ``cfg.generator = "host"`` opts out — the device
 rasteriser ``shifu_terrain_generate``: the host only draws each tile's few
 random parameters (same numpy stream as the host builder), one launch writes the whole map and a
 second one the spawn origins; bit-identical to the host builder over the stand-in generators.
