@@ -52,7 +52,7 @@ struct A1K {
   int n_feet, feet[4];
   float feet_thr, air_cmd_min, air_dt;
   int air_reset;
-  // term lists of the two B warps of the pipelined kernel (host-side cost balance)
+  // term lists of the B warps of the pipelined kernel (host-side cost balance)
   int term_count[A1K_TERM_WARPS], term_list[A1K_TERM_WARPS][SHIFU_MAX_REWARD_TERMS];
   float contact_thr_sq;
   // scan table

@@ -176,8 +176,7 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
     k.rp_thr_sq[i] = sqrt_threshold(p1);
   }
   k.contact_thr_sq = sqrt_threshold(d.contact_term_force);
-  // Split of the term list over the two B warps of the pipelined kernel: longest-processing-time
-  // greedy on rough per-term instruction counts; warp 0 also carries the yaw normalisation (~60).
+  // constants of the dof-limit / feet-air-time terms
   for (int i = 0; i < A1_DOF; ++i) { k.dof_lo[i] = d.dof_pos_limit_low[i]; k.dof_hi[i] = d.dof_pos_limit_high[i]; }
   if (d.num_feet < 0 || d.num_feet > 4) return fail(SHIFU_E_RANGE, "num_feet=%d out of range", d.num_feet);
   k.n_feet = d.num_feet;
@@ -191,7 +190,9 @@ static int fill_a1k(const ShifuA1Desc& d, A1K& k) {
   // longest-processing-time split of the term list over the B warps of the pipelined kernel.  Warp 0
   // starts loaded with the yaw normalisation it does first (~115 on the scale of term_cost, from the
   // phase timers); with terms-only warps present, warps 0 and 1 also carry their B2 halves (~100
-  // each), which a terms-only warp overlaps with the next tile's terms.
+  // and ~160 with the carried body-frame rows), which a terms-only warp overlaps with the next tile's
+  // terms.  The preloads were tuned on the B200 (profiles/README.md: a dozen other splits of the
+  // reference's six terms are 0.5-8 % slower).
   int load[A1K_TERM_WARPS] = {0}, order[SHIFU_MAX_REWARD_TERMS];
   load[0] = V3_BG_WARPS > 2 ? V3_LOAD0 : 60; load[1] = V3_BG_WARPS > 2 ? V3_LOAD1 : 0;
   for (int i = 0; i < k.n_terms; ++i) order[i] = i;
