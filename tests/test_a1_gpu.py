@@ -213,6 +213,25 @@ def test_exact_division_variant_matches_oracle():
         util.compare_a1(util.cuda_a1_outputs(hp), util.oracle_a1_outputs(st), f"hscale0.13/s{t}")
 
 
+def test_without_terrain_curriculum_matches_oracle():
+    """cfg.terrain.curriculum = False (a1_conditional.py:117-118): resets keep level and origin."""
+    from oracle import shifu_oracle as so
+    from shifu_b200.sim.synthetic import a1_snapshot
+    n = 32 * 11 + 7
+    hs, origins, types, env_origins = _terrain(n)
+    p, st = util.make_oracle_a1(n, hs, origins, types, env_origins, curriculum=False)
+    hp = util.make_cuda_a1(n, hs, origins, types, env_origins, curriculum=False)
+    so.a1_reset(p, st, a1_snapshot(8, 0, n, p_base=0.2))
+    hp.reset_idx(None)
+    util.cuda_a1_step(hp, a1_snapshot(8, 0, n, p_base=0.2), torch.zeros(n, 12))
+    for t in range(1, 4):
+        snap = a1_snapshot(8, t, n, p_base=0.2)
+        so.a1_step(p, st, snap.actions, snap)
+        util.cuda_a1_step(hp, snap, snap.actions)
+        util.compare_a1(util.cuda_a1_outputs(hp), util.oracle_a1_outputs(st), f"no-curriculum/s{t}")
+    assert int(st.reset.sum()) > 0 and int(st.terrain_levels.abs().sum()) == 0
+
+
 def test_asymmetric_point_grid_matches_oracle():
     """The pipelined kernel rotates once per point PAIR, which needs measured_points symmetric about the
     base; any other 17x11 grid (here: shifted forward, uneven rows) must be routed to the phased kernel

@@ -55,11 +55,12 @@ def assert_close(name: str, got, want, exact: bool):
 
 def make_oracle_a1(n, height_samples, terrain_origins, terrain_types, env_origins, *, border_size=25,
                    max_terrain_level=10, num_cols=20, rng_seed=0x5EED, env_offset=0, horizontal_scale=0.1,
-                   points_x=None, points_y=None):
+                   points_x=None, points_y=None, curriculum=True):
     from oracle import shifu_oracle as so
     grid = {k: list(v) for k, v in (("points_x", points_x), ("points_y", points_y)) if v is not None}
     p = so.A1Params(n=n, border_size=border_size, max_terrain_level=max_terrain_level, num_cols=num_cols,
-                    rng_seed=rng_seed, env_offset=env_offset, horizontal_scale=horizontal_scale, **grid)
+                    rng_seed=rng_seed, env_offset=env_offset, horizontal_scale=horizontal_scale, curriculum=curriculum,
+                    **grid)
     st = so.a1_new_state(p, torch.as_tensor(height_samples), torch.as_tensor(terrain_origins).float(),
                          torch.as_tensor(terrain_types), torch.as_tensor(env_origins).float())
     return p, st
@@ -89,7 +90,7 @@ def oracle_a1_outputs(st) -> Dict[str, np.ndarray]:
 
 def make_cuda_a1(n, height_samples, terrain_origins, terrain_types, env_origins, *, border_size=25.,
                  max_terrain_level=10, num_cols=20, rng_seed=0x5EED, env_offset=0, carry=False, device="cuda:0",
-                 horizontal_scale=0.1, want_measured_heights=True, points_x=None, points_y=None):
+                 horizontal_scale=0.1, want_measured_heights=True, points_x=None, points_y=None, curriculum=True):
     from shifu_b200 import hotpath
     grid = {k: tuple(v) for k, v in (("points_x", points_x), ("points_y", points_y)) if v is not None}
     dev = torch.device(device)
@@ -99,7 +100,7 @@ def make_cuda_a1(n, height_samples, terrain_origins, terrain_types, env_origins,
     contact = torch.zeros(n * 17, 3, device=dev)
     desc = hotpath.a1_desc(n, border_size=float(border_size), max_terrain_level=max_terrain_level,
                            num_terrain_types=num_cols, rng_seed=rng_seed, env_offset=env_offset,
-                           horizontal_scale=horizontal_scale, **grid)
+                           horizontal_scale=horizontal_scale, curriculum=curriculum, **grid)
     hp = hotpath.A1HotPath(desc, root_state=root, dof_state=dof, contact_state=contact,
                            height_samples=torch.as_tensor(height_samples),
                            terrain_origins=torch.as_tensor(terrain_origins),
