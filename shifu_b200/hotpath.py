@@ -394,6 +394,7 @@ class A1HotPath(_StepStats):
         self.step_counter = 0
         self._init_stats(dev)
         self._graph, self._graph_warm, self._dev_step, self._graph_actions = None, 0, -1, None
+        self._fork = None
         self.carry_body_frame = carry_body_frame
         self._io = None
         nv.check(self.lib.shifu_set_height_map(self.ctx.handle, nv.ptr(self.height_samples),
@@ -528,10 +529,22 @@ class A1HotPath(_StepStats):
         if not self.carry_body_frame:
             self.body_frame()
         self.post_physics(use_step_dev)
-        self.compact()
+        main = torch.cuda.current_stream()
+        if torch.cuda.is_current_stream_capturing():
+            # inside the step graph the id compaction and the statistics collect / publish are independent
+            # branches after the fused kernel: two latency-bound tails run side by side
+            if self._fork is None:
+                self._fork = torch.cuda.Stream(device=self.device)
+            self._fork.wait_stream(main)
+            with torch.cuda.stream(self._fork):
+                self.compact()
+        else:
+            self.compact()
         self._collect(use_step_dev)
         if publish:
             self._publish(allreduce, from_step_dev=use_step_dev)
+        if torch.cuda.is_current_stream_capturing():
+            main.wait_stream(self._fork)
 
     # -- the same step as ONE CUDA-graph replay (launch-bound small-N configurations) -----------
     def graph_step(self, raw_actions: torch.Tensor, decimation: int = 4, allreduce=None):
