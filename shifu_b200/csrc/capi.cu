@@ -12,6 +12,7 @@
 #include "a1_kernels.cuh"
 #include "a1_fused.cuh"
 #include "a1_fused_tma.cuh"
+#include "scan_pairs.cuh"
 #include "abb_kernels.cuh"
 #include "arm_ik.cuh"
 #include "camera_gather.cuh"
@@ -422,6 +423,13 @@ extern "C" int shifu_get_heights(ShifuCtx* c, const float* root, float* mh, int3
   if (!c->is_a1) return fail(SHIFU_E_STATE, "shifu_get_heights needs an A1 ctx");
   if (c->d_table == nullptr) return fail(SHIFU_E_STATE, "call shifu_set_height_map first");
   const int tiles = (c->a1.num_envs + A1_TILE - 1) / A1_TILE;
+  if (cell_idx == nullptr && c->a1k.tiled && !c->a1k.exact_div && c->grid_symmetric &&
+      !(getenv("SHIFU_A1_KERNEL") != nullptr && strcmp(getenv("SHIFU_A1_KERNEL"), "phased") == 0)) {
+    const int cap4 = c->sm_count * 4;                   // packed, one rotation per point pair (scan_pairs.cuh)
+    get_heights_pairs_kernel<<<tiles < cap4 ? tiles : cap4, SP_THREADS, 0, S(stream)>>>(c->a1k, root, mh);
+    CUDA_TRY(cudaGetLastError());
+    return SHIFU_OK;
+  }
   const int cap = c->sm_count * 8;
   get_heights_kernel<<<tiles < cap ? tiles : cap, A1_THREADS, 0, S(stream)>>>(c->a1k, root, mh, cell_idx);
   CUDA_TRY(cudaGetLastError());

@@ -132,6 +132,28 @@ def test_height_cell_indices_bit_exact():
         del os.environ["SHIFU_TABLE_LAYOUT"]
 
 
+@pytest.mark.parametrize("n", [1, 31, 33, 4096 + 17, 65536])
+def test_get_heights_fast_path_matches_oracle(n):
+    """shifu_get_heights without the cell-index output takes the packed pair-rotation kernel
+    (csrc/scan_pairs.cuh): heights bit-identical to the oracle and to the scalar kernel, ragged sizes and
+    robots pushed off the map included."""
+    from oracle import shifu_oracle as so
+    from shifu_b200.sim.synthetic import a1_snapshot
+    hs, origins, types, env_origins = _terrain(n)
+    hp = util.make_cuda_a1(n, hs, origins, types, env_origins)
+    root = a1_snapshot(7, 2, n).root_offset.clone()
+    root[:, :3] += env_origins
+    root[::7, 0] -= 300.0                                   # off the map: indices clip to 0 ...
+    root[3::11, 1] += 500.0                                 # ... and to the last cell
+    hp.root_state.copy_(root.cuda())
+    fast = hp.get_heights(out=torch.full((n, 187), -7.0, device="cuda")).cpu()
+    idx = torch.zeros(n * 187, 2, dtype=torch.int32, device="cuda")
+    slow = hp.get_heights(out=torch.zeros(n, 187, device="cuda"), cell_idx=idx).cpu()
+    p = so.A1Params(n=n)
+    want = so.get_heights(p, root[:, :7], torch.from_numpy(hs), p.height_points())
+    assert torch.equal(fast, want) and torch.equal(slow, want)
+
+
 def test_pd_torque_and_body_frame():
     from oracle import shifu_oracle as so
     from shifu_b200.sim.synthetic import a1_snapshot
